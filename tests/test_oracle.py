@@ -1,0 +1,148 @@
+"""Pin the CPU oracle (oracle/pyci_oracle.c) against golden vectors produced by the reference's own
+compiled sources (tests/golden/make_golden.py) and against the energies hard-coded in the reference's
+tests (pyci/test/test_routines.py:41-45).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import datafile, seeded_vec, sha
+from oracle import oracle as O
+
+SMALL = [("h4_sto3g", "fullci", (2, 2)), ("lih_sto6g", "fullci", (2, 2)), ("BH_sto-3g_eq", "fullci", (3, 3)),
+         ("h6_sto_3g", "fullci", (4, 2)), ("be_ccpvdz", "doci", (2, 2)), ("h2_sto3g", "fullci", (1, 1))]
+KIND = {"doci": O.DOCI, "fullci": O.FULLCI, "genci": O.GENCI}
+
+
+def load(fn, kind):
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
+    return ecore, one.shape[0], ints
+
+
+@pytest.mark.parametrize("fn,kind,occ", SMALL)
+def test_oracle_small_csr_bit_exact(small, fn, kind, occ):
+    ecore, n, ints = load(fn, kind)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    dets = O.all_dets(KIND[kind], n, *occ)
+    assert np.array_equal(dets, small[tag + ".dets"])
+    x = seeded_vec(len(dets), 11)
+    for name, kw in (("sym", dict(symmetric=True)), ("nonsym", dict(symmetric=False)),
+                     ("rect", dict(nrow=len(dets) - 10, symmetric=False))):
+        if tag + f".{name}.indptr" not in small:
+            continue
+        ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, **kw)
+        assert np.array_equal(ip, small[f"{tag}.{name}.indptr"])
+        assert np.array_equal(ix, small[f"{tag}.{name}.indices"])
+        assert np.array_equal(dv, small[f"{tag}.{name}.data"])  # bit-exact values
+        y = O.matvec(ip, ix, dv, x, name == "sym")
+        np.testing.assert_allclose(y, small[f"{tag}.{name}.y"], rtol=0, atol=1e-12)
+    ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints)
+    e0, _ = O.lowest_eigenpair(ip, ix, dv, len(dets))
+    assert abs(e0 + ecore - float(small[tag + ".E0"])) < 1e-10
+
+
+@pytest.mark.parametrize("fn,kind,occ", SMALL)
+def test_oracle_small_rdms_bit_exact(small, fn, kind, occ):
+    _, n, _ = load(fn, kind)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    dets = small[tag + ".dets"]
+    c = seeded_vec(len(dets), 12)
+    c /= np.linalg.norm(c)
+    r1, r2 = O.compute_rdms(KIND[kind], n, occ[0], occ[1], dets, c)
+    assert np.array_equal(r1, small[tag + ".rdm1"])
+    assert np.array_equal(r2, small[tag + ".rdm2"])
+
+
+def test_oracle_selected_space(small):
+    _, one, two = O.synthetic_integrals(8, 1234)
+    dets = small["syn8.fullci32.sel.dets"]
+    for name, sym in (("sym", True), ("nonsym", False)):
+        ip, ix, dv = O.sparse_op(O.FULLCI, 8, 3, 2, dets, (one, two), symmetric=sym)
+        assert np.array_equal(ip, small[f"syn8.fullci32.sel.{name}.indptr"])
+        assert np.array_equal(ix, small[f"syn8.fullci32.sel.{name}.indices"])
+        assert np.array_equal(dv, small[f"syn8.fullci32.sel.{name}.data"])
+    c = seeded_vec(len(dets), 12)
+    c /= np.linalg.norm(c)
+    r1, r2 = O.compute_rdms(O.FULLCI, 8, 3, 2, dets, c)
+    assert np.array_equal(r1, small["syn8.fullci32.sel.rdm1"])
+    assert np.array_equal(r2, small["syn8.fullci32.sel.rdm2"])
+
+
+@pytest.mark.parametrize("fn,kind,occ,pinned", [
+    ("be_ccpvdz", "fullci", (2, 2), -14.617409507),   # BASELINE config 1, test_routines.py:44
+    ("h2o_ccpvdz", "doci", (5, 5), -75.634588422),    # BASELINE config 2, test_routines.py:45
+    ("li2_ccpvdz", "doci", (3, 3), -14.878455349),    # test_routines.py:41
+])
+def test_oracle_configs_digest_and_energy(digests, fn, kind, occ, pinned):
+    ecore, n, ints = load(fn, kind)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    dets = O.all_dets(KIND[kind], n, *occ)
+    g = digests[tag + ".sym"]
+    assert len(dets) == g["ndet"]
+    ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints)
+    assert (len(ix), sha(ip), sha(ix), sha(dv)) == (g["nnz"], g["indptr"], g["indices"], g["data"])
+    e0, c = O.lowest_eigenpair(ip, ix, dv, len(dets))
+    assert abs(e0 + ecore - g["E0"]) < 1e-10
+    assert abs(e0 + ecore - pinned) < 1e-9       # the reference's own tolerance
+    y = O.matvec(ip, ix, dv, seeded_vec(len(dets), 11), True)
+    assert abs(np.linalg.norm(y) - g["y_norm"]) < 1e-9 * g["y_norm"]
+    gn = digests[tag + ".nonsym"]
+    ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, symmetric=False)
+    assert (len(ix), sha(ip), sha(ix), sha(dv)) == (gn["nnz"], gn["indptr"], gn["indices"], gn["data"])
+    cc = seeded_vec(len(dets), 12)
+    cc /= np.linalg.norm(cc)
+    r1, r2 = O.compute_rdms(KIND[kind], n, occ[0], occ[1], dets, cc)
+    assert (sha(r1), sha(r2)) == (digests[tag + ".rdm"]["rdm1"], digests[tag + ".rdm"]["rdm2"])
+
+
+def test_oracle_multiword_and_unequal_spin(digests):
+    _, one, two = O.synthetic_integrals(66, 7)
+    dets = O.all_dets(O.DOCI, 66, 2)
+    ip, ix, dv = O.sparse_op(O.DOCI, 66, 2, 2, dets, O.senzero_integrals(one, two))
+    g = digests["syn66.doci22.sym"]
+    assert (len(ix), sha(ip), sha(ix), sha(dv)) == (g["nnz"], g["indptr"], g["indices"], g["data"])
+    _, one, two = O.synthetic_integrals(9, 1234)
+    dets = O.all_dets(O.FULLCI, 9, 4, 3)
+    ip, ix, dv = O.sparse_op(O.FULLCI, 9, 4, 3, dets, (one, two))
+    g = digests["syn9.fullci43.sym"]
+    assert (len(ix), sha(ip), sha(ix), sha(dv)) == (g["nnz"], g["indptr"], g["indices"], g["data"])
+
+
+@pytest.mark.parametrize("fn,occ", [("h4_sto3g", (2, 2)), ("BH_sto-3g_eq", (3, 3)), ("h6_sto_3g", (4, 2))])
+def test_oracle_genci(genci_golden, fn, occ):
+    """GenCI: (i) equals the reference compiled with the two loop bounds fixed, (ii) equals FullCI on the
+    spatial integrals bit-for-bit, (iii) RDMs equal the spin-expanded FullCI RDMs."""
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    n = one.shape[0]
+    fd = O.all_dets(O.FULLCI, n, *occ)
+    gd = (fd[:, 0, :] | (fd[:, 1, :] << np.uint64(n))).astype(np.uint64)
+    tag = f"{fn}.genci{sum(occ)}"
+    assert np.array_equal(gd, genci_golden[tag + ".dets"])
+    h2, g2 = O.spin_orbital_integrals(one, two)
+    for name, sym in (("sym", True), ("nonsym", False)):
+        got = O.sparse_op(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), symmetric=sym)
+        for a, key in zip(got, ("indptr", "indices", "data")):
+            assert np.array_equal(a, genci_golden[f"{tag}.{name}.{key}"])
+        full = O.sparse_op(O.FULLCI, n, occ[0], occ[1], fd, (one, two), symmetric=sym)
+        for a, b in zip(got, full):
+            assert np.array_equal(a, b)
+    c = seeded_vec(len(fd), 2)
+    c /= np.linalg.norm(c)
+    s1, s2 = O.spinize_rdms(*O.compute_rdms(O.FULLCI, n, occ[0], occ[1], fd, c))
+    g1, g2r = O.compute_rdms(O.GENCI, 2 * n, sum(occ), 0, gd, c)
+    np.testing.assert_allclose(g1, s1, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(g2r, s2, rtol=0, atol=1e-14)
+
+
+def test_oracle_rdm_energy_identity():
+    """E = ecore + sum h g1 + 1/4 sum <pq||rs> G2 (test_routines.py:130-133) on Be/cc-pVDZ DOCI and H4 FullCI."""
+    for fn, kind, occ in (("be_ccpvdz", "doci", (2, 2)), ("h4_sto3g", "fullci", (2, 2))):
+        ecore, n, ints = load(fn, kind)
+        _, one, two = O.read_fcidump(datafile(fn))
+        dets = O.all_dets(KIND[kind], n, *occ)
+        ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints)
+        e0, c = O.lowest_eigenpair(ip, ix, dv, len(dets))
+        r1, r2 = O.spinize_rdms(*O.compute_rdms(KIND[kind], n, occ[0], occ[1], dets, c))
+        h2, g2 = O.spin_orbital_integrals(one, two)
+        anti = g2 - g2.transpose(0, 1, 3, 2)
+        e = ecore + np.einsum("ij,ij", h2, r1) + 0.25 * np.einsum("ijkl,ijkl", anti, r2)
+        assert abs(e - (e0 + ecore)) < 1e-9
