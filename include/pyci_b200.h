@@ -1,0 +1,164 @@
+/*
+ * pyci_b200 -- C ABI of the B200 (sm_100a) CI-Hamiltonian hot path.
+ *
+ * This is the drop-in boundary beneath the reference's pybind11 module `pyci._pyci`
+ * (/root/reference/pyci/src/binding.cpp:29): plain pointers and sizes, opaque handles, int status,
+ * no exceptions and no torch/pybind types.  The host module `pyci_b200._pyci` (C++/pybind11, same
+ * class and method names as the reference) binds exactly these entry points; INTEGRATION.md shows
+ * the equivalent stub a PyCI maintainer would add.  Citations are relative to /root/reference.
+ *
+ * All `long` are int64.  Host pointers unless a name ends in `_dev`.  Every function returns
+ * PYCI_OK or a negative status; pyci_last_error() gives the message of the calling thread's last
+ * failure.  There is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ * with PYCI_ERR_CUDA.
+ */
+#ifndef PYCI_B200_H
+#define PYCI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYCI_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PYCI_API __attribute__((visibility("default")))
+#else
+#define PYCI_API
+#endif
+
+/* status codes; the pybind11 layer maps them to the reference's exception types
+ * (wfn.cpp:52-57, sparseop.cpp:117-119,136) */
+enum {
+    PYCI_OK = 0,
+    PYCI_ERR_VALUE = -1,   /* std::invalid_argument / domain_error -> ValueError   */
+    PYCI_ERR_TYPE = -2,    /* pybind11::type_error                 -> TypeError    */
+    PYCI_ERR_RUNTIME = -3, /* std::runtime_error ("did not converge") -> RuntimeError */
+    PYCI_ERR_CUDA = -4,    /* CUDA / NCCL failure, no device       -> RuntimeError */
+    PYCI_ERR_MEMORY = -5,  /* device or host allocation failed     -> MemoryError  */
+    PYCI_ERR_UNSUPPORTED = -6 /* valid for the reference, not on device (nbasis > 64) -> RuntimeError */
+};
+
+/* wave-function kinds: DOCIWfn / FullCIWfn / GenCIWfn (pyci.h:496-619) */
+enum { PYCI_DOCI = 0, PYCI_FULLCI = 1, PYCI_GENCI = 2 };
+
+typedef struct pyci_ctx pyci_ctx; /* one device + stream (+ NCCL communicator when row-sharded) */
+typedef struct pyci_ham pyci_ham; /* SQuantOp integrals resident in HBM          (pyci.h:285-302) */
+typedef struct pyci_wfn pyci_wfn; /* determinant array + GPU hash index          (pyci.h:306-330) */
+typedef struct pyci_op pyci_op;   /* SparseOp: CSR row shard resident in HBM     (pyci.h:621-693) */
+
+PYCI_API const char *pyci_last_error(void);
+PYCI_API int pyci_abi_version(void);
+/* number of visible CUDA devices (0 when there is none); never fails */
+PYCI_API int pyci_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to launch on (e.g. torch's current stream), or
+ * NULL to let the context create its own non-blocking stream. */
+PYCI_API int pyci_ctx_create(int device, void *stream, pyci_ctx **out);
+PYCI_API void pyci_ctx_destroy(pyci_ctx *ctx);
+PYCI_API int pyci_ctx_synchronize(pyci_ctx *ctx);
+/* Row-sharding across `nranks` processes (one per GPU of one box).  unique_id: the 128 bytes of an
+ * ncclUniqueId made by pyci_nccl_unique_id() on rank 0 and handed to the other ranks by the caller
+ * (torch.distributed broadcast, MPI, a file ...).  Collective: every rank must call it. */
+PYCI_API int pyci_nccl_unique_id(void *unique_id_128);
+PYCI_API int pyci_ctx_init_comm(pyci_ctx *ctx, int rank, int nranks, const void *unique_id_128);
+PYCI_API int pyci_ctx_rank(const pyci_ctx *ctx);
+PYCI_API int pyci_ctx_nranks(const pyci_ctx *ctx);
+/* Number of this library's kernels launched through ctx since creation / since the last reset. */
+PYCI_API long pyci_ctx_launch_count(const pyci_ctx *ctx);
+PYCI_API void pyci_ctx_reset_launch_count(pyci_ctx *ctx);
+
+/* ---- Hamiltonian: SQuantOp (squantop.cpp:163-183) --------------------------------------------- */
+
+/* one_mo[n*n], two_mo[n^4] (physicist order <ik|jl> at i*n^3+k*n^2+j*n+l), h[n], v[n*n], w[n*n]. */
+PYCI_API int pyci_ham_upload(pyci_ctx *ctx, long nbasis, double ecore, const double *one_mo,
+                    const double *two_mo, const double *h, const double *v, const double *w,
+                    pyci_ham **out);
+PYCI_API void pyci_ham_destroy(pyci_ham *ham);
+
+/* ---- wave function: determinant storage + index_det (onespinwfn.cpp:123-126, twospinwfn.cpp:129-132) */
+
+/* dets: [ndet][nword] (DOCI, GenCI) or [ndet][2][nword] (FullCI) uint64 bit-strings, nword =
+ * ceil(nbasis/64) (common.cpp:280-282).  Builds the open-addressing GPU hash keyed by the bit-string.
+ * Device kernels handle nword == 1; larger nbasis returns PYCI_ERR_UNSUPPORTED.  Duplicate
+ * determinants return PYCI_ERR_VALUE. */
+PYCI_API int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
+                    const uint64_t *dets, pyci_wfn **out);
+PYCI_API void pyci_wfn_destroy(pyci_wfn *wfn);
+/* index_det for a batch of determinants (same layout as dets); out[i] = row index or -1 */
+PYCI_API int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out);
+
+/* ---- sparse operator: SparseOp (sparseop.cpp) --------------------------------------------------- */
+
+/* SparseOp::SparseOp + update (sparseop.cpp:49-71,186-201): rows [0,nrow) x columns [0,ncol) of H
+ * in the determinant basis of wfn; nrow/ncol < 0 mean ndet.  symmetric != 0 gives the operator the
+ * reference's lower-triangular export; on the device the full rows are kept for a gather SpMV.
+ * With a communicator, rank r owns the contiguous row block r of ceil(nrow/nranks) rows. */
+PYCI_API int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
+                  int symmetric, pyci_op **out);
+PYCI_API void pyci_op_destroy(pyci_op *op);
+
+PYCI_API long pyci_op_nrow(const pyci_op *op);
+PYCI_API long pyci_op_ncol(const pyci_op *op);
+/* first row and number of rows held by this rank */
+PYCI_API long pyci_op_row_begin(const pyci_op *op);
+PYCI_API long pyci_op_row_count(const pyci_op *op);
+/* SparseOp::size of this rank's rows in the REFERENCE's storage (lower triangle + diagonal when symmetric) */
+PYCI_API long pyci_op_size(const pyci_op *op);
+/* non-zeros this rank streams per SpMV (full rows) */
+PYCI_API long pyci_op_stored_nnz(const pyci_op *op);
+PYCI_API double pyci_op_ecore(const pyci_op *op);
+/* device seconds of the last build on this rank: [0] hash index, [1] count+scan, [2] fill+sort, [3] total */
+PYCI_API int pyci_op_build_times(const pyci_op *op, double *seconds4);
+
+/* py_indptr / py_indices / py_data (sparseop.cpp:504-514) for this rank's rows, in the reference's
+ * layout: indptr[row_count+1] starting at 0, indices int64, data fp64, each row sorted by column
+ * (sparseop.cpp:214-218). */
+PYCI_API int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data);
+
+/* SparseOp::perform_op (sparseop.cpp:96-112): y[nrow] = A x[ncol]; ecore is not applied.
+ * Host buffers; with a communicator every rank passes the full x and receives the full y. */
+PYCI_API int pyci_op_matvec(pyci_op *op, const double *x, double *y);
+/* Same on device buffers: x_dev[ncol] full, y_dev[row_count] this rank's rows; asynchronous on the
+ * context's stream; no collective. */
+PYCI_API int pyci_op_matvec_dev(pyci_op *op, const double *x_dev, double *y_dev);
+/* Measurement helper: `warmup` untimed + `reps` timed launches of the SpMV kernel on a device-resident
+ * pseudo-random x, each timed with CUDA events on the context's stream; ms[reps] receives the per-launch
+ * device times.  flush_bytes > 0 overwrites a scratch buffer of that size before every launch (evicts L2). */
+PYCI_API int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, double *ms);
+/* SparseOp::get_element (sparseop.cpp:89-94); i must be a row of this rank */
+PYCI_API int pyci_op_get_element(pyci_op *op, long i, long j, double *out);
+
+typedef struct pyci_solve_stats {
+    long matvecs;        /* SpMV launches */
+    long iterations;     /* Davidson iterations */
+    long restarts;
+    double residual;     /* max residual norm of the returned pairs */
+    double seconds;      /* device seconds inside the solver */
+    double spmv_seconds; /* of which SpMV (+ all-gather) */
+} pyci_solve_stats;
+
+/* SparseOp::solve_ci (sparseop.cpp:114-146): n lowest eigenpairs, evals[n] (ecore added),
+ * evecs[n][nrow] row-major.  c0: nrow doubles or NULL; ncv: subspace size or -1 for
+ * min(nrow, max(2n+1, 20)); maxiter: -1 for 10*n*nrow; tol: residual tolerance relative to
+ * max(eps^(2/3), |theta|) as in Spectra.  Errors follow sparseop.cpp:116-124,136.
+ * Collective when row-sharded (NCCL all-gather of the trial vector every iteration). */
+PYCI_API int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long maxiter, double tol,
+                  double *evals, double *evecs, pyci_solve_stats *stats);
+
+/* ---- reduced density matrices: compute_rdms (rdm.cpp:20-65, 269-530, 532-632) ------------------- */
+
+/* DOCI: rdm1 = d0[n*n], rdm2 = d2[n*n].  FullCI: rdm1[2*n*n] (aa,bb), rdm2[3*n^4] (aaaa,bbbb,abab).
+ * GenCI: rdm1[n*n], rdm2[n^4] (fully antisymmetric; the reference routine is defective).
+ * Collective when row-sharded (all-reduce of the tensors). */
+PYCI_API int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1,
+                      double *rdm2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCI_B200_H */

@@ -1,0 +1,658 @@
+// C-ABI entry points of libpyci_b200.so (include/pyci_b200.h): argument checking with the
+// reference's error behaviour, HBM allocation, host<->device staging, and dispatch to the kernels.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+int wfn_index_dets_impl(pyci_wfn *wfn, long n, const u64 *dets_dev, long *out_dev);
+
+static thread_local char g_error[1024] = "";
+
+void pyci_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int ctx_activate(const pyci_ctx *ctx) {
+    PYCI_CUDA(cudaSetDevice(ctx->device));
+    return PYCI_OK;
+}
+
+namespace {
+
+long binom_l(long n, long k) {
+    if (k < 0 || k > n)
+        return 0;
+    if (k > n - k)
+        k = n - k;
+    __int128 b = 1;
+    for (long d = 1; d <= k; ++d) {
+        b = b * (n - k + d) / d;
+        if (b > (__int128)1 << 62)
+            return INT64_MAX;
+    }
+    return (long)b;
+}
+
+template<class T>
+int upload(T **dst, const T *src, size_t count, cudaStream_t st) {
+    PYCI_CUDA(cudaMalloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
+    if (count)
+        PYCI_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, st));
+    return PYCI_OK;
+}
+
+__global__ void export_lower_kernel(const long *__restrict__ indptr, const int *__restrict__ cols,
+                                    const double *__restrict__ vals, const int *__restrict__ take,
+                                    const long *__restrict__ outptr, long *__restrict__ out_idx,
+                                    double *__restrict__ out_val, long nrows) {
+    // one warp per row copies the first take[r] entries (all of them when take == nullptr)
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r = warp; r < nrows; r += nwarps) {
+        const long src = indptr[r], dst = outptr[r];
+        const long cnt = outptr[r + 1] - dst;
+        for (long e = lane; e < cnt; e += 32) {
+            out_idx[dst + e] = cols[src + e];
+            out_val[dst + e] = vals[src + e];
+        }
+    }
+}
+
+__global__ void prefix_from_counts(const int *cnt, long n, long *out) {
+    // single thread block sequential-by-chunks scan (export path only; n = rows of one shard)
+    __shared__ long carry;
+    __shared__ long ws[32];
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    for (long base = 0; base < n; base += blockDim.x) {
+        const long i = base + threadIdx.x;
+        const long v = (i < n) ? cnt[i] : 0;
+        long x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long t = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o)
+                x += t;
+        }
+        if ((threadIdx.x & 31) == 31)
+            ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            long t = (threadIdx.x < (blockDim.x >> 5)) ? ws[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const long q = __shfl_up_sync(0xffffffffu, t, o);
+                if (threadIdx.x >= o)
+                    t += q;
+            }
+            ws[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const long woff = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+        const long incl = x + woff + carry;
+        if (i < n)
+            out[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1)
+            carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        out[n] = carry;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *pyci_last_error(void) { return g_error; }
+
+int pyci_abi_version(void) { return PYCI_B200_ABI_VERSION; }
+
+int pyci_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pyci_ctx_create(int device, void *stream, pyci_ctx **out) {
+    if (!out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        PYCI_FAIL(PYCI_ERR_CUDA, "no CUDA device available (%s); pyci_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev)
+        PYCI_FAIL(PYCI_ERR_VALUE, "device %d out of range (%d visible)", device, ndev);
+    PYCI_CUDA(cudaSetDevice(device));
+    pyci_ctx *ctx = new pyci_ctx();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            delete ctx;
+            PYCI_CUDA(se);
+        }
+        ctx->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    PYCI_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int i = 0; i < 4; ++i)
+        PYCI_CUDA(cudaEventCreate(&ctx->ev[i]));
+    *out = ctx;
+    return PYCI_OK;
+}
+
+void pyci_ctx_destroy(pyci_ctx *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    comm_destroy(ctx);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->ev[i])
+            cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pyci_ctx_synchronize(pyci_ctx *ctx) {
+    PYCI_TRY(ctx_activate(ctx));
+    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PYCI_OK;
+}
+
+int pyci_nccl_unique_id(void *unique_id_128) { return comm_unique_id(unique_id_128); }
+
+int pyci_ctx_init_comm(pyci_ctx *ctx, int rank, int nranks, const void *unique_id_128) {
+    PYCI_TRY(ctx_activate(ctx));
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        PYCI_FAIL(PYCI_ERR_VALUE, "bad rank %d of %d", rank, nranks);
+    if (nranks == 1) {
+        ctx->rank = 0;
+        ctx->nranks = 1;
+        return PYCI_OK;
+    }
+    return comm_init(ctx, rank, nranks, unique_id_128);
+}
+
+int pyci_ctx_rank(const pyci_ctx *ctx) { return ctx->rank; }
+int pyci_ctx_nranks(const pyci_ctx *ctx) { return ctx->nranks; }
+long pyci_ctx_launch_count(const pyci_ctx *ctx) { return ctx->launches; }
+void pyci_ctx_reset_launch_count(pyci_ctx *ctx) { ctx->launches = 0; }
+
+// ---- Hamiltonian -------------------------------------------------------------------------------
+
+int pyci_ham_upload(pyci_ctx *ctx, long nbasis, double ecore, const double *one_mo, const double *two_mo,
+                    const double *h, const double *v, const double *w, pyci_ham **out) {
+    if (!ctx || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (nbasis < 1)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nbasis must be positive");
+    PYCI_TRY(ctx_activate(ctx));
+    pyci_ham *ham = new pyci_ham();
+    ham->ctx = ctx;
+    ham->nbasis = nbasis;
+    ham->ecore = ecore;
+    const size_t n1 = (size_t)nbasis, n2 = n1 * n1;
+    int rc = PYCI_OK;
+    if (one_mo && rc == PYCI_OK)
+        rc = upload(&ham->one_mo, one_mo, n2, ctx->stream);
+    if (two_mo && rc == PYCI_OK)
+        rc = upload(&ham->two_mo, two_mo, n2 * n2, ctx->stream);
+    if (h && rc == PYCI_OK)
+        rc = upload(&ham->h, h, n1, ctx->stream);
+    if (v && rc == PYCI_OK)
+        rc = upload(&ham->v, v, n2, ctx->stream);
+    if (w && rc == PYCI_OK)
+        rc = upload(&ham->w, w, n2, ctx->stream);
+    if (rc == PYCI_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        pyci_set_error("CUDA error while uploading integrals: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = PYCI_ERR_CUDA;
+    }
+    if (rc != PYCI_OK) {
+        pyci_ham_destroy(ham);
+        return rc;
+    }
+    *out = ham;
+    return PYCI_OK;
+}
+
+void pyci_ham_destroy(pyci_ham *ham) {
+    if (!ham)
+        return;
+    cudaSetDevice(ham->ctx->device);
+    cudaFree(ham->one_mo);
+    cudaFree(ham->two_mo);
+    cudaFree(ham->h);
+    cudaFree(ham->v);
+    cudaFree(ham->w);
+    delete ham;
+}
+
+// ---- wave function -----------------------------------------------------------------------------
+
+int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
+                    const uint64_t *dets, pyci_wfn **out) {
+    if (!ctx || !out || (ndet > 0 && !dets))
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (kind != PYCI_DOCI && kind != PYCI_FULLCI && kind != PYCI_GENCI)
+        PYCI_FAIL(PYCI_ERR_VALUE, "unknown wave-function kind %d", kind);
+    // Wfn::init checks (wfn.cpp:52-57) and the per-class ones (dociwfn.cpp:28, genciwfn.cpp:50)
+    if (nocc_dn < 0)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nocc_dn is < 0");
+    if (nocc_up < nocc_dn)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nocc_up is < nocc_dn");
+    if (nbasis < nocc_up)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nbasis is < nocc_up");
+    if (kind == PYCI_DOCI && nocc_up != nocc_dn)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nocc_up != nocc_dn");
+    if (kind == PYCI_GENCI && nocc_dn != 0)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nocc_dn != 0");
+    if (nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
+                  "nbasis = %ld needs multi-word determinants; the device kernels handle nbasis <= 64", nbasis);
+    if (ndet < 0 || ndet >= (1L << 31) - 1)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
+    PYCI_TRY(ctx_activate(ctx));
+    const int nwords = (kind == PYCI_FULLCI) ? 2 : 1;
+    // every string must hold the declared number of electrons inside nbasis orbitals
+    const u64 valid = (nbasis == 64) ? ~0ULL : ((1ULL << nbasis) - 1ULL);
+    for (long i = 0; i < ndet; ++i) {
+        const u64 a = dets[i * nwords], b = (nwords == 2) ? dets[i * nwords + 1] : 0ULL;
+        if ((a & ~valid) || (b & ~valid) || __builtin_popcountll(a) != nocc_up ||
+            (nwords == 2 && __builtin_popcountll(b) != nocc_dn))
+            PYCI_FAIL(PYCI_ERR_VALUE, "determinant %ld does not have the declared occupation", i);
+    }
+    pyci_wfn *wfn = new pyci_wfn();
+    wfn->ctx = ctx;
+    wfn->kind = kind;
+    wfn->nbasis = nbasis;
+    wfn->nocc_up = nocc_up;
+    wfn->nocc_dn = nocc_dn;
+    wfn->ndet = ndet;
+    wfn->nwords = nwords;
+    if (kind == PYCI_FULLCI)
+        wfn->keymode = (nbasis <= 16) ? KEY32 : (nbasis <= 32) ? KEY64 : KEY128;
+    else
+        wfn->keymode = (nbasis <= 32) ? KEY32 : KEY64;
+    const long full = (kind == PYCI_FULLCI)
+                          ? ((binom_l(nbasis, nocc_up) < (1L << 31) && binom_l(nbasis, nocc_dn) < (1L << 31))
+                                 ? binom_l(nbasis, nocc_up) * binom_l(nbasis, nocc_dn)
+                                 : INT64_MAX)
+                          : binom_l(nbasis, nocc_up);
+    wfn->complete = (ndet == full); // uniqueness is verified by the index build
+    int rc = upload(&wfn->dets, (const u64 *)dets, (size_t)ndet * nwords, ctx->stream);
+    if (rc == PYCI_OK)
+        rc = wfn_build_index(wfn);
+    if (rc != PYCI_OK) {
+        pyci_wfn_destroy(wfn);
+        return rc;
+    }
+    *out = wfn;
+    return PYCI_OK;
+}
+
+void pyci_wfn_destroy(pyci_wfn *wfn) {
+    if (!wfn)
+        return;
+    cudaSetDevice(wfn->ctx->device);
+    cudaFree(wfn->dets);
+    cudaFree(wfn->slots);
+    delete wfn;
+}
+
+int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) {
+    if (!wfn || (n > 0 && (!dets || !out)))
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (n <= 0)
+        return PYCI_OK;
+    pyci_ctx *ctx = wfn->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    u64 *d = nullptr;
+    long *o = nullptr;
+    PYCI_TRY(upload(&d, (const u64 *)dets, (size_t)n * wfn->nwords, ctx->stream));
+    cudaError_t e = cudaMalloc(&o, sizeof(long) * n);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        PYCI_CUDA(e);
+    }
+    int rc = wfn_index_dets_impl(wfn, n, d, o);
+    if (rc == PYCI_OK) {
+        e = cudaMemcpyAsync(out, o, sizeof(long) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            pyci_set_error("CUDA error: %s", cudaGetErrorString(e));
+            rc = PYCI_ERR_CUDA;
+        }
+    }
+    cudaFree(d);
+    cudaFree(o);
+    return rc;
+}
+
+// ---- sparse operator -----------------------------------------------------------------------------
+
+int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol, int symmetric,
+                  pyci_op **out) {
+    if (!ctx || !ham || !wfn || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *out = nullptr;
+    if (ham->nbasis != wfn->nbasis)
+        PYCI_FAIL(PYCI_ERR_VALUE, "ham.nbasis (%ld) != wfn.nbasis (%ld)", ham->nbasis, wfn->nbasis);
+    if (nrow < 0)
+        nrow = wfn->ndet; // sparseop.cpp:53-54
+    if (ncol < 0)
+        ncol = wfn->ndet;
+    if (nrow > wfn->ndet || ncol > wfn->ndet)
+        PYCI_FAIL(PYCI_ERR_VALUE, "nrow/ncol (%ld, %ld) exceed the number of determinants (%ld)", nrow, ncol,
+                  wfn->ndet);
+    if (wfn->kind == PYCI_DOCI ? (!ham->h || !ham->v || !ham->w) : (!ham->one_mo || !ham->two_mo))
+        PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian lacks the integrals this wave-function kind needs");
+    PYCI_TRY(ctx_activate(ctx));
+    pyci_op *op = new pyci_op();
+    op->ctx = ctx;
+    op->nrow = nrow;
+    op->ncol = ncol;
+    op->symmetric = symmetric ? 1 : 0;
+    op->ecore = ham->ecore;
+    const long R = ctx->nranks;
+    op->npad = std::max<long>(1, (std::max(nrow, ncol) + R - 1) / R);
+    op->row0 = std::min(nrow, op->npad * ctx->rank);
+    op->nloc = std::min(nrow, op->npad * (ctx->rank + 1)) - op->row0;
+    int rc = PYCI_OK;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (rc == PYCI_OK && cudaMalloc(p, std::max<size_t>(bytes, 8)) != cudaSuccess) {
+            pyci_set_error("device allocation of %zu bytes failed", bytes);
+            cudaGetLastError();
+            rc = PYCI_ERR_MEMORY;
+        }
+    };
+    alloc((void **)&op->indptr, sizeof(long) * (size_t)(op->nloc + 1));
+    alloc((void **)&op->lowcnt, sizeof(int) * (size_t)(op->nloc + 1));
+    alloc((void **)&op->diag, sizeof(double) * (size_t)op->npad);
+    if (rc == PYCI_OK) {
+        cudaMemsetAsync(op->lowcnt, 0, sizeof(int) * (size_t)(op->nloc + 1), ctx->stream);
+        cudaMemsetAsync(op->diag, 0, sizeof(double) * (size_t)op->npad, ctx->stream);
+        rc = op_build_impl(ctx, ham, wfn, op);
+    }
+    if (rc != PYCI_OK) {
+        pyci_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return PYCI_OK;
+}
+
+void pyci_op_destroy(pyci_op *op) {
+    if (!op)
+        return;
+    cudaSetDevice(op->ctx->device);
+    cudaFree(op->indptr);
+    cudaFree(op->cols);
+    cudaFree(op->vals);
+    cudaFree(op->lowcnt);
+    cudaFree(op->diag);
+    cudaFree(op->xbuf);
+    cudaFree(op->ybuf);
+    delete op;
+}
+
+long pyci_op_nrow(const pyci_op *op) { return op->nrow; }
+long pyci_op_ncol(const pyci_op *op) { return op->ncol; }
+long pyci_op_row_begin(const pyci_op *op) { return op->row0; }
+long pyci_op_row_count(const pyci_op *op) { return op->nloc; }
+long pyci_op_size(const pyci_op *op) { return op->size_ref; }
+long pyci_op_stored_nnz(const pyci_op *op) { return op->nnz; }
+double pyci_op_ecore(const pyci_op *op) { return op->ecore; }
+
+int pyci_op_build_times(const pyci_op *op, double *seconds4) {
+    for (int i = 0; i < 4; ++i)
+        seconds4[i] = op->times[i];
+    return PYCI_OK;
+}
+
+int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
+    if (!op || !indptr)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    cudaStream_t st = ctx->stream;
+    const long nloc = op->nloc;
+    if (!op->symmetric && !indices && !data) {
+        PYCI_CUDA(cudaMemcpyAsync(indptr, op->indptr, sizeof(long) * (nloc + 1), cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        return PYCI_OK;
+    }
+    // output row pointer: the full row (general) or its col <= row prefix (symmetric, sparseop.cpp:223,262,431)
+    long *outptr = nullptr;
+    PYCI_CUDA(cudaMalloc(&outptr, sizeof(long) * (size_t)(nloc + 1)));
+    if (op->symmetric) {
+        prefix_from_counts<<<1, 1024, 0, st>>>(op->lowcnt, nloc, outptr);
+        ctx->launches++;
+    } else {
+        PYCI_CUDA(cudaMemcpyAsync(outptr, op->indptr, sizeof(long) * (nloc + 1), cudaMemcpyDeviceToDevice, st));
+    }
+    PYCI_CUDA(cudaMemcpyAsync(indptr, outptr, sizeof(long) * (nloc + 1), cudaMemcpyDeviceToHost, st));
+    PYCI_CUDA(cudaStreamSynchronize(st));
+    const long total = indptr[nloc];
+    int rc = PYCI_OK;
+    if ((indices || data) && total > 0) {
+        // widen to the reference's int64 indices on the device in bounded chunks of rows
+        const long chunk_entries = 1L << 26; // 64 Mi entries -> 1 GiB of staging
+        long *didx = nullptr;
+        double *dval = nullptr;
+        const long cap = std::min(total, chunk_entries + (long)INT32_MAX / 2);
+        long r0 = 0;
+        while (r0 < nloc && rc == PYCI_OK) {
+            long r1 = r0;
+            while (r1 < nloc && indptr[r1 + 1] - indptr[r0] <= chunk_entries)
+                ++r1;
+            if (r1 == r0)
+                r1 = r0 + 1; // a single very long row
+            const long cnt = indptr[r1] - indptr[r0];
+            if (cnt > 0) {
+                if (!didx) {
+                    const long c = std::max(cnt, std::min(cap, chunk_entries));
+                    PYCI_CUDA(cudaMalloc(&didx, sizeof(long) * (size_t)c));
+                    PYCI_CUDA(cudaMalloc(&dval, sizeof(double) * (size_t)c));
+                }
+                // outptr shifted so that this chunk starts at 0 of the staging buffers
+                export_lower_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(op->indptr + r0, op->cols, op->vals, nullptr,
+                                                                       outptr + r0, didx - indptr[r0],
+                                                                       dval - indptr[r0], r1 - r0);
+                ctx->launches++;
+                if (indices)
+                    PYCI_CUDA(cudaMemcpyAsync(indices + indptr[r0], didx, sizeof(long) * cnt, cudaMemcpyDeviceToHost, st));
+                if (data)
+                    PYCI_CUDA(cudaMemcpyAsync(data + indptr[r0], dval, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+                PYCI_CUDA(cudaStreamSynchronize(st));
+            }
+            r0 = r1;
+        }
+        cudaFree(didx);
+        cudaFree(dval);
+    }
+    cudaFree(outptr);
+    return rc;
+}
+
+int pyci_op_matvec_dev(pyci_op *op, const double *x_dev, double *y_dev) {
+    if (!op || !x_dev || !y_dev)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(op->ctx));
+    if (op->symmetric && op->nrow != op->ncol)
+        PYCI_FAIL(PYCI_ERR_TYPE, "symmetric operator must be square for matvec");
+    return spmv_launch(op, x_dev, y_dev);
+}
+
+int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
+    if (!op || !x || !y)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    if (op->symmetric && op->nrow != op->ncol)
+        PYCI_FAIL(PYCI_ERR_TYPE, "symmetric operator must be square for matvec");
+    const long R = ctx->nranks;
+    if (!op->xbuf)
+        PYCI_CUDA(cudaMalloc(&op->xbuf, sizeof(double) * (size_t)std::max<long>(op->ncol, 1)));
+    if (!op->ybuf) {
+        PYCI_CUDA(cudaMalloc(&op->ybuf, sizeof(double) * (size_t)(op->npad * (R + 1))));
+        PYCI_CUDA(cudaMemsetAsync(op->ybuf, 0, sizeof(double) * (size_t)(op->npad * (R + 1)), ctx->stream));
+    }
+    PYCI_CUDA(cudaMemcpyAsync(op->xbuf, x, sizeof(double) * op->ncol, cudaMemcpyHostToDevice, ctx->stream));
+    double *yloc = op->ybuf + op->npad * R; // local shard, then gathered into ybuf[0 .. npad*R)
+    PYCI_TRY(spmv_launch(op, op->xbuf, yloc));
+    const double *ysrc = yloc;
+    if (R > 1) {
+        PYCI_TRY(comm_allgather_f64(ctx, yloc, op->ybuf, op->npad));
+        ysrc = op->ybuf;
+    }
+    PYCI_CUDA(cudaMemcpyAsync(y, ysrc, sizeof(double) * op->nrow, cudaMemcpyDeviceToHost, ctx->stream));
+    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PYCI_OK;
+}
+
+int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, double *ms) {
+    if (!op || !ms || reps < 1)
+        PYCI_FAIL(PYCI_ERR_VALUE, "bad argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    cudaStream_t st = ctx->stream;
+    double *x = nullptr, *y = nullptr;
+    void *flush = nullptr;
+    const long nx = std::max<long>(op->ncol, 1);
+    PYCI_CUDA(cudaMalloc(&x, sizeof(double) * nx));
+    PYCI_CUDA(cudaMalloc(&y, sizeof(double) * std::max<long>(op->nloc, 1)));
+    if (flush_bytes > 0)
+        PYCI_CUDA(cudaMalloc(&flush, (size_t)flush_bytes));
+    std::vector<double> hx((size_t)nx);
+    u64 sdd = 0x9e3779b97f4a7c15ULL;
+    for (long i = 0; i < nx; ++i) {
+        sdd ^= sdd << 13; sdd ^= sdd >> 7; sdd ^= sdd << 17;
+        hx[i] = (double)(sdd >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+    }
+    PYCI_CUDA(cudaMemcpyAsync(x, hx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+    std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+    for (auto &e : ev)
+        PYCI_CUDA(cudaEventCreate(&e));
+    int rc = PYCI_OK;
+    for (int it = -warmup; it < reps && rc == PYCI_OK; ++it) {
+        if (flush)
+            cudaMemsetAsync(flush, it & 0xff, (size_t)flush_bytes, st);
+        if (it >= 0)
+            cudaEventRecord(ev[2 * it], st);
+        rc = spmv_launch(op, x, y);
+        if (it >= 0)
+            cudaEventRecord(ev[2 * it + 1], st);
+    }
+    if (rc == PYCI_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        pyci_set_error("CUDA error in SpMV timing: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = PYCI_ERR_CUDA;
+    }
+    for (int it = 0; it < reps && rc == PYCI_OK; ++it) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ev[2 * it], ev[2 * it + 1]);
+        ms[it] = t;
+    }
+    for (auto &e : ev)
+        cudaEventDestroy(e);
+    cudaFree(x);
+    cudaFree(y);
+    cudaFree(flush);
+    return rc;
+}
+
+int pyci_op_get_element(pyci_op *op, long i, long j, double *out) {
+    if (!op || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    if (i < op->row0 || i >= op->row0 + op->nloc)
+        PYCI_FAIL(PYCI_ERR_VALUE, "row %ld is not held by this rank", i);
+    *out = 0.0;
+    long ptr[2];
+    PYCI_CUDA(cudaMemcpyAsync(ptr, op->indptr + (i - op->row0), sizeof(long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    const long m = ptr[1] - ptr[0];
+    if (m <= 0)
+        return PYCI_OK;
+    std::vector<int> cols((size_t)m);
+    PYCI_CUDA(cudaMemcpyAsync(cols.data(), op->cols + ptr[0], sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    // symmetric storage of the reference only holds j <= i (sparseop.cpp:89-94 searches the stored row)
+    if (op->symmetric && j > i)
+        return PYCI_OK;
+    auto it = std::lower_bound(cols.begin(), cols.end(), (int)std::min<long>(j, INT32_MAX));
+    if (it != cols.end() && *it == j) {
+        PYCI_CUDA(cudaMemcpyAsync(out, op->vals + ptr[0] + (it - cols.begin()), sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return PYCI_OK;
+}
+
+int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long maxiter, double tol, double *evals,
+                  double *evecs, pyci_solve_stats *stats) {
+    if (!op || !evals || !evecs)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    if (stats)
+        memset(stats, 0, sizeof(*stats));
+    const long nrow = op->nrow;
+    // guards of SparseOp::solve_ci, sparseop.cpp:116-124
+    if (n < 1 || (nrow > 1 && n >= nrow) || (nrow == 1 && n > 1))
+        PYCI_FAIL(PYCI_ERR_VALUE, "cannot find >=n eigenpairs for sparse operator with n rows");
+    if (nrow != op->ncol)
+        PYCI_FAIL(PYCI_ERR_TYPE, "Can only solve sparse symmetric matrix operators");
+    if (nrow == 1) {
+        double h00 = 0.0;
+        if (ctx->rank == 0)
+            PYCI_CUDA(cudaMemcpy(&h00, op->diag, sizeof(double), cudaMemcpyDeviceToHost));
+        if (ctx->nranks > 1) {
+            // every rank must return the same value; rank 0 holds row 0
+            double *d = nullptr;
+            PYCI_CUDA(cudaMalloc(&d, sizeof(double)));
+            PYCI_CUDA(cudaMemcpy(d, &h00, sizeof(double), cudaMemcpyHostToDevice));
+            PYCI_TRY(comm_allreduce_sum_f64(ctx, d, 1));
+            PYCI_CUDA(cudaMemcpy(&h00, d, sizeof(double), cudaMemcpyDeviceToHost));
+            cudaFree(d);
+        }
+        evals[0] = h00 + op->ecore;
+        evecs[0] = 1.0;
+        return PYCI_OK;
+    }
+    return solve_impl(op, n, c0, ncv, maxiter, tol, evals, evecs, stats);
+}
+
+int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2) {
+    if (!ctx || !wfn || !coeffs || !rdm1 || !rdm2)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(ctx));
+    return rdms_impl(ctx, wfn, coeffs, rdm1, rdm2);
+}
+
+} // extern "C"

@@ -1,0 +1,141 @@
+// NCCL plumbing for the row-sharded operator: one communicator per context (one process per GPU of
+// one box), used for the per-iteration all-gather of the trial vector and the small all-reduces of
+// the Davidson solver and the RDM tensors.  libnccl.so.2 is resolved lazily with dlopen so that the
+// single-GPU path has no NCCL dependency and so that, inside a torch process, the copy of NCCL that
+// torch already loaded is the one that is used.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi &api() {
+    static NcclApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle)
+                break;
+        }
+        if (!a.handle) {
+            a.why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+            return;
+        }
+#define LOAD(sym)                                                                                  \
+    a.sym = reinterpret_cast<decltype(a.sym)>(dlsym(a.handle, "nccl" #sym));                       \
+    if (!a.sym) {                                                                                  \
+        a.why = "libnccl lacks nccl" #sym;                                                         \
+        return;                                                                                    \
+    }
+        LOAD(GetUniqueId)
+        LOAD(CommInitRank)
+        LOAD(CommDestroy)
+        LOAD(AllGather)
+        LOAD(AllReduce)
+        LOAD(GetErrorString)
+#undef LOAD
+        a.ok = true;
+    });
+    return a;
+}
+
+#define PYCI_NCCL(expr)                                                                            \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        if (_r != ncclSuccess) {                                                                   \
+            pyci_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, api().GetErrorString(_r)); \
+            return PYCI_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+int need_api() {
+    if (!api().ok)
+        PYCI_FAIL(PYCI_ERR_CUDA, "%s", api().why.c_str());
+    return PYCI_OK;
+}
+
+} // namespace
+
+int comm_unique_id(void *out128) {
+    PYCI_TRY(need_api());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    PYCI_NCCL(api().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return PYCI_OK;
+}
+
+int comm_init(pyci_ctx *ctx, int rank, int nranks, const void *id128) {
+    PYCI_TRY(need_api());
+    if (!id128)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null NCCL unique id");
+    if (ctx->comm)
+        comm_destroy(ctx);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    PYCI_NCCL(api().CommInitRank(&comm, nranks, id, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return PYCI_OK;
+}
+
+void comm_destroy(pyci_ctx *ctx) {
+    if (ctx->comm && api().ok)
+        api().CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+}
+
+int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, long count_per_rank) {
+    if (ctx->nranks == 1) {
+        if (send_dev != recv_dev)
+            PYCI_CUDA(cudaMemcpyAsync(recv_dev, send_dev, sizeof(double) * count_per_rank, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+        return PYCI_OK;
+    }
+    PYCI_NCCL(api().AllGather(send_dev, recv_dev, (size_t)count_per_rank, ncclDouble, (ncclComm_t)ctx->comm,
+                              ctx->stream));
+    return PYCI_OK;
+}
+
+int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count) {
+    if (ctx->nranks == 1)
+        return PYCI_OK;
+    PYCI_NCCL(api().AllReduce(buf_dev, buf_dev, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)ctx->comm,
+                              ctx->stream));
+    return PYCI_OK;
+}
+
+int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count) {
+    if (ctx->nranks == 1)
+        return PYCI_OK;
+    long *d = nullptr;
+    PYCI_CUDA(cudaMalloc(&d, sizeof(long) * count));
+    PYCI_CUDA(cudaMemcpyAsync(d, vals, sizeof(long) * count, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = api().AllReduce(d, d, (size_t)count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
+    if (r == ncclSuccess) {
+        cudaMemcpyAsync(vals, d, sizeof(long) * count, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d);
+    PYCI_NCCL(r);
+    return PYCI_OK;
+}

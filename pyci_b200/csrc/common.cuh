@@ -1,0 +1,255 @@
+// Shared declarations of the pyci_b200 CUDA library (sm_100a only).
+// Host-side structs behind the opaque C-ABI handles of include/pyci_b200.h, error plumbing, and the
+// device-side determinant primitives (the device restatement of /root/reference/pyci/src/common.cpp).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pyci_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+
+void pyci_set_error(const char *fmt, ...);
+
+#define PYCI_CUDA(expr)                                                                            \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            pyci_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                           cudaGetErrorString(_e));                                                \
+            return (_e == cudaErrorMemoryAllocation) ? PYCI_ERR_MEMORY : PYCI_ERR_CUDA;            \
+        }                                                                                          \
+    } while (0)
+
+#define PYCI_TRY(expr)                                                                             \
+    do {                                                                                           \
+        int _s = (expr);                                                                           \
+        if (_s != PYCI_OK)                                                                         \
+            return _s;                                                                             \
+    } while (0)
+
+#define PYCI_FAIL(code, ...)                                                                       \
+    do {                                                                                           \
+        pyci_set_error(__VA_ARGS__);                                                               \
+        return (code);                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handles
+
+struct pyci_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int rank = 0, nranks = 1;
+    void *comm = nullptr; // ncclComm_t
+    long launches = 0;
+    int sm_count = 148;
+    int smem_optin = 0; // max dynamic shared memory per block (opt-in)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct pyci_ham {
+    pyci_ctx *ctx = nullptr;
+    long nbasis = 0;
+    double ecore = 0.0;
+    double *one_mo = nullptr, *two_mo = nullptr, *h = nullptr, *v = nullptr, *w = nullptr;
+};
+
+// how determinant strings are packed into hash keys
+enum KeyMode {
+    KEY32 = 0,  // one u32: one-spin nbasis<=32, or two-spin nbasis<=16 as alpha | beta<<nbasis   ( 8 B slots)
+    KEY64 = 1,  // one u64: one-spin nbasis<=64, or two-spin nbasis<=32 as alpha | beta<<nbasis   (16 B slots)
+    KEY128 = 2  // two u64 (alpha, beta): two-spin 32<nbasis<=64                                  (32 B slots)
+};
+
+struct pyci_wfn {
+    pyci_ctx *ctx = nullptr;
+    int kind = 0;
+    long nbasis = 0, nocc_up = 0, nocc_dn = 0, ndet = 0;
+    int nwords = 1;       // u64 words per determinant in `dets` (1 one-spin, 2 two-spin)
+    int keymode = KEY64;
+    bool complete = false; // ndet equals the size of the full space => every excitation is present
+    u64 *dets = nullptr;   // [ndet][nwords]
+    void *slots = nullptr; // hash slots (layout by keymode)
+    u32 mask = 0;          // capacity-1 (capacity is a power of two)
+    double hash_seconds = 0.0;
+};
+
+struct pyci_op {
+    pyci_ctx *ctx = nullptr;
+    long nrow = 0, ncol = 0; // global shape
+    long row0 = 0, nloc = 0; // this rank's rows [row0, row0+nloc)
+    long npad = 0;           // rows per rank (uniform), npad*nranks >= nrow
+    int symmetric = 0;
+    double ecore = 0.0;
+    long nnz = 0;            // stored non-zeros (full rows)
+    long size_ref = 0;       // SparseOp::size in the reference's storage for these rows
+    long *indptr = nullptr;  // [nloc+1] device, int64
+    int *cols = nullptr;     // [nnz] device, int32
+    double *vals = nullptr;  // [nnz] device, fp64
+    int *lowcnt = nullptr;   // [nloc] entries with col <= row (sorted rows => a prefix)
+    double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
+    double times[4] = {0, 0, 0, 0};
+    // scratch for host-facing matvec
+    double *xbuf = nullptr, *ybuf = nullptr;
+};
+
+int ctx_activate(const pyci_ctx *ctx);
+
+// nccl (loaded lazily with dlopen; see comm.cpp)
+int comm_unique_id(void *out128);
+int comm_init(pyci_ctx *ctx, int rank, int nranks, const void *id128);
+void comm_destroy(pyci_ctx *ctx);
+int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, long count_per_rank);
+int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count);
+int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
+
+// build.cu
+int wfn_build_index(pyci_wfn *wfn);
+int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
+// spmv.cu
+int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev);
+// solver.cu
+int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, double tol,
+               double *evals, double *evecs, pyci_solve_stats *stats);
+// rdm.cu
+int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2);
+
+// ---------------------------------------------------------------------------------------------
+// device primitives
+
+#ifdef __CUDACC__
+
+// 64-bit finaliser of MurmurHash3 / 32-bit finaliser: the hash of the GPU determinant index
+__device__ __forceinline__ u32 mix32(u32 h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ u32 mix64(u64 h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return (u32)h;
+}
+
+struct __align__(8) Slot32 {
+    u32 key;
+    int val;
+};
+struct __align__(16) Slot64 {
+    u64 key;
+    int val;
+    int pad;
+};
+struct __align__(32) Slot128 {
+    u64 k0, k1;
+    int val;
+    int pad[3];
+};
+
+// Determinant index: the device form of Wfn::index_det (onespinwfn.cpp:123-126, twospinwfn.cpp:129-132).
+// a = alpha string (or the only string), b = beta string (0 for one-spin), shift = nbasis (two-spin packing).
+template<int KM>
+struct DetIndex;
+
+template<>
+struct DetIndex<KEY32> {
+    const Slot32 *slots;
+    u32 mask;
+    int shift;
+    __device__ __forceinline__ u32 key(u64 a, u64 b) const { return (u32)a | ((u32)b << shift); }
+    __device__ __forceinline__ u32 home(u32 k) const { return mix32(k) & mask; }
+    __device__ __forceinline__ int find(u64 a, u64 b) const {
+        const u32 k = key(a, b);
+        u32 p = home(k);
+        for (;;) {
+            const uint2 s = __ldg(reinterpret_cast<const uint2 *>(slots + p));
+            if ((int)s.y < 0)
+                return -1;
+            if (s.x == k)
+                return (int)s.y;
+            p = (p + 1) & mask;
+        }
+    }
+};
+
+template<>
+struct DetIndex<KEY64> {
+    const Slot64 *slots;
+    u32 mask;
+    int shift;
+    __device__ __forceinline__ u64 key(u64 a, u64 b) const { return a | (b << shift); }
+    __device__ __forceinline__ u32 home(u64 k) const { return mix64(k) & mask; }
+    __device__ __forceinline__ int find(u64 a, u64 b) const {
+        const u64 k = key(a, b);
+        u32 p = home(k);
+        for (;;) {
+            const uint4 s = __ldg(reinterpret_cast<const uint4 *>(slots + p));
+            if ((int)s.z < 0)
+                return -1;
+            if ((((u64)s.y << 32) | s.x) == k)
+                return (int)s.z;
+            p = (p + 1) & mask;
+        }
+    }
+};
+
+template<>
+struct DetIndex<KEY128> {
+    const Slot128 *slots;
+    u32 mask;
+    int shift;
+    __device__ __forceinline__ u32 home(u64 a, u64 b) const {
+        return mix64(a ^ (b * 0x9e3779b97f4a7c15ULL) ^ (b >> 29)) & mask;
+    }
+    __device__ __forceinline__ int find(u64 a, u64 b) const {
+        u32 p = home(a, b);
+        for (;;) {
+            const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(slots + p));
+            const int v = __ldg(reinterpret_cast<const int *>(slots + p) + 4);
+            if (v < 0)
+                return -1;
+            if ((((u64)s0.y << 32) | s0.x) == a && (((u64)s0.w << 32) | s0.z) == b)
+                return v;
+            p = (p + 1) & mask;
+        }
+    }
+};
+
+// bits strictly between positions lo < hi of one 64-bit string
+__device__ __forceinline__ u64 between_mask(int lo, int hi) {
+    return ((1ULL << hi) - 1ULL) & ~((2ULL << lo) - 1ULL);
+}
+
+// phase_single_det (common.cpp:163-194): parity of the occupied orbitals strictly between i and a,
+// evaluated on the un-excited string.  Returns 0 for +1, 1 for -1.
+__device__ __forceinline__ int parity_single(u64 det, int i, int a) {
+    const int lo = min(i, a), hi = max(i, a);
+    return __popcll(det & between_mask(lo, hi)) & 1;
+}
+
+// phase_double_det (common.cpp:196-261): both single parities on the original string plus one flip
+// when (i2 < a1) or (i1 > a2) (:258-259).  Callers pass i1 < i2 and a1 < a2.
+__device__ __forceinline__ int parity_double(u64 det, int i1, int i2, int a1, int a2) {
+    return (parity_single(det, i1, a1) + parity_single(det, i2, a2) + ((i2 < a1) || (i1 > a2))) & 1;
+}
+
+__device__ __forceinline__ double apply_sign(double x, int parity) { return parity ? -x : x; }
+
+#endif // __CUDACC__

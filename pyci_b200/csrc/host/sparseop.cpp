@@ -1,0 +1,232 @@
+// sparse_op / compute_rdms of pyci_b200._pyci: numpy marshalling around the C ABI, with the method
+// names, defaults and error behaviour of the reference's SparseOp
+// (/root/reference/pyci/src/sparseop.cpp:49-178,504-514; binding.cpp:884-1088) and py_compute_rdms_*
+// (rdm.cpp:1011-1055).  All numerical work happens in libpyci_b200.so on the GPU.
+#include <cstdlib>
+#include <cstring>
+
+#include "pyci_host.h"
+
+namespace pyci_host {
+
+namespace {
+
+pyci_ctx *g_ctx = nullptr;
+
+struct DeviceHam {
+    pyci_ham *h = nullptr;
+    DeviceHam(const SQuantOp &ham) {
+        check(pyci_ham_upload(device_context(), ham.nbasis, ham.ecore, ham.one_mo(), ham.two_mo(),
+                              ham.h_array.data(), ham.v_array.data(), ham.w_array.data(), &h));
+    }
+    ~DeviceHam() { pyci_ham_destroy(h); }
+};
+
+struct DeviceWfn {
+    pyci_wfn *w = nullptr;
+    DeviceWfn(const Wfn &wfn) {
+        if (wfn.dict.size() != wfn.ndet)
+            throw std::invalid_argument("wave function contains duplicate determinants");
+        check(pyci_wfn_upload(device_context(), wfn.kind(), wfn.nbasis, wfn.nocc_up, wfn.nocc_dn, wfn.ndet,
+                              reinterpret_cast<const uint64_t *>(wfn.dets.data()), &w));
+    }
+    ~DeviceWfn() { pyci_wfn_destroy(w); }
+};
+
+} // namespace
+
+void check(int status) {
+    if (status == PYCI_OK)
+        return;
+    const std::string msg = pyci_last_error();
+    switch (status) {
+    case PYCI_ERR_VALUE:
+        throw std::invalid_argument(msg);
+    case PYCI_ERR_TYPE:
+        throw py::type_error(msg);
+    case PYCI_ERR_MEMORY:
+        throw std::bad_alloc();
+    default:
+        throw std::runtime_error(msg);
+    }
+}
+
+pyci_ctx *device_context() {
+    if (!g_ctx) {
+        int device = 0;
+        const char *env = std::getenv("PYCI_B200_DEVICE");
+        if (!env)
+            env = std::getenv("LOCAL_RANK");
+        if (env)
+            device = std::atoi(env);
+        check(pyci_ctx_create(device, nullptr, &g_ctx));
+    }
+    return g_ctx;
+}
+
+void set_device_context(int device, uintptr_t stream) {
+    if (g_ctx) {
+        pyci_ctx_destroy(g_ctx);
+        g_ctx = nullptr;
+    }
+    check(pyci_ctx_create(device, reinterpret_cast<void *>(stream), &g_ctx));
+}
+
+SparseOp::SparseOp(const SQuantOp &ham, const Wfn &wfn, long rows, long cols, bool symm)
+    : nrow((rows > -1) ? rows : wfn.ndet), ncol((cols > -1) ? cols : wfn.ndet), ecore(ham.ecore), symmetric(symm) {
+    build(ham, wfn, nrow, ncol);
+}
+
+SparseOp::~SparseOp() { pyci_op_destroy(handle); }
+
+void SparseOp::build(const SQuantOp &ham, const Wfn &wfn, long rows, long cols) {
+    DeviceHam dham(ham);
+    DeviceWfn dwfn(wfn);
+    pyci_op *fresh = nullptr;
+    pyci_ctx *ctx = device_context();
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_op_build(ctx, dham.h, dwfn.w, rows, cols, symmetric ? 1 : 0, &fresh);
+    }
+    check(rc);
+    pyci_op_destroy(handle);
+    handle = fresh;
+    nrow = rows;
+    ncol = cols;
+    ecore = ham.ecore;
+    size = pyci_op_size(handle);
+    shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
+}
+
+// SparseOp::py_update (sparseop.cpp:175-178): extend to all determinants now in wfn.  The reference
+// appends rows [old nrow, ndet) to its lower-triangular storage; the device keeps full rows, so the
+// operator is rebuilt -- the exported CSR is identical.
+void SparseOp::update(const SQuantOp &ham, const Wfn &wfn) { build(ham, wfn, wfn.ndet, wfn.ndet); }
+
+double SparseOp::get_element(long i, long j) const {
+    if (i < 0 || i >= nrow || j < 0 || j >= ncol)
+        throw py::index_error("matrix index out of range");
+    double v = 0.0;
+    check(pyci_op_get_element(handle, i, j, &v));
+    return v;
+}
+
+Array<double> SparseOp::py_matvec(const Array<double> x) const {
+    Array<double> y(nrow);
+    return py_matvec_out(x, y);
+}
+
+Array<double> SparseOp::py_matvec_out(const Array<double> x, Array<double> y) const {
+    if ((long)x.size() < ncol)
+        throw std::invalid_argument("x has fewer elements than the operator has columns");
+    if ((long)y.size() < nrow)
+        throw std::invalid_argument("out has fewer elements than the operator has rows");
+    const double *xp = x.data();
+    double *yp = y.mutable_data();
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_op_matvec(handle, xp, yp);
+    }
+    check(rc);
+    return y;
+}
+
+py::tuple SparseOp::py_solve_ci(long n, py::object c0, long ncv, long maxiter, double tol) {
+    if (n < 1)
+        throw std::invalid_argument("cannot find >=n eigenpairs for sparse operator with n rows");
+    Array<double> eigvals(n);
+    Array<double> eigvecs({n, nrow});
+    Array<double> guess;
+    const double *cptr = nullptr;
+    if (!c0.is_none()) {
+        guess = c0.cast<Array<double>>();
+        if ((long)guess.size() < nrow)
+            throw std::invalid_argument("c0 has fewer elements than the operator has rows");
+        cptr = guess.data();
+    }
+    double *ev = eigvals.mutable_data(), *ec = eigvecs.mutable_data();
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_op_solve(handle, n, cptr, ncv, maxiter, tol, ev, ec, &last_stats);
+    }
+    check(rc);
+    return py::make_tuple(eigvals, eigvecs);
+}
+
+Array<long> SparseOp::py_indptr() const {
+    Array<long> a(pyci_op_row_count(handle) + 1);
+    check(pyci_op_export_csr(handle, a.mutable_data(), nullptr, nullptr));
+    return a;
+}
+
+Array<long> SparseOp::py_indices() const {
+    std::vector<long> ptr((size_t)pyci_op_row_count(handle) + 1);
+    Array<long> a(pyci_op_size(handle));
+    check(pyci_op_export_csr(handle, ptr.data(), a.mutable_data(), nullptr));
+    return a;
+}
+
+Array<double> SparseOp::py_data() const {
+    std::vector<long> ptr((size_t)pyci_op_row_count(handle) + 1);
+    Array<double> a(pyci_op_size(handle));
+    check(pyci_op_export_csr(handle, ptr.data(), nullptr, a.mutable_data()));
+    return a;
+}
+
+py::dict SparseOp::py_stats() const {
+    py::dict d;
+    double t[4];
+    pyci_op_build_times(handle, t);
+    d["hash_seconds"] = t[0];
+    d["count_seconds"] = t[1];
+    d["fill_seconds"] = t[2];
+    d["build_seconds"] = t[3];
+    d["stored_nnz"] = pyci_op_stored_nnz(handle);
+    d["row_begin"] = pyci_op_row_begin(handle);
+    d["row_count"] = pyci_op_row_count(handle);
+    d["matvecs"] = last_stats.matvecs;
+    d["iterations"] = last_stats.iterations;
+    d["restarts"] = last_stats.restarts;
+    d["residual"] = last_stats.residual;
+    d["solve_seconds"] = last_stats.seconds;
+    d["spmv_seconds"] = last_stats.spmv_seconds;
+    return d;
+}
+
+// py_compute_rdms_{doci,fullci,genci} (rdm.cpp:1011-1055): output shapes follow the reference
+py::tuple py_compute_rdms(const Wfn &wfn, const Array<double> coeffs) {
+    if ((long)coeffs.size() < wfn.ndet)
+        throw std::invalid_argument("coeffs has fewer elements than the wave function has determinants");
+    const long n = wfn.nbasis;
+    Array<double> r1, r2;
+    switch (wfn.kind()) {
+    case PYCI_DOCI:
+        r1 = Array<double>({n, n});
+        r2 = Array<double>({n, n});
+        break;
+    case PYCI_FULLCI:
+        r1 = Array<double>({2L, n, n});
+        r2 = Array<double>({3L, n, n, n, n});
+        break;
+    default:
+        r1 = Array<double>({n, n});
+        r2 = Array<double>({n, n, n, n});
+        break;
+    }
+    DeviceWfn dwfn(wfn);
+    const double *cp = coeffs.data();
+    double *p1 = r1.mutable_data(), *p2 = r2.mutable_data();
+    pyci_ctx *ctx = device_context();
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_compute_rdms(ctx, dwfn.w, cp, p1, p2);
+    }
+    check(rc);
+    return py::make_tuple(r1, r2);
+}
+
+} // namespace pyci_host

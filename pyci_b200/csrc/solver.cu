@@ -1,0 +1,503 @@
+// Lowest eigenpairs of the CI matrix on the device: the B200 replacement for SparseOp::solve_ci
+// (/root/reference/pyci/src/sparseop.cpp:114-146), which hands the matrix to Spectra's
+// implicitly-restarted Lanczos.  Here: block Davidson with the diagonal preconditioner, the subspace
+// vectors row-sharded like the matrix, one SpMV (spmv.cu) per new vector, and -- when the rows are
+// sharded over several GPUs -- one NCCL all-gather of the trial vector per SpMV plus small
+// all-reduces of the projected quantities.  The small projected eigenproblem (subspace dimension
+// <= ncv) is diagonalised on the host with cyclic Jacobi.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RB = 256; // threads per block of the vector kernels
+constexpr int KCHUNK = 8;
+
+// out[j] += sum_i V[j*ld + i] * w[i], j < k <= KCHUNK
+__global__ void __launch_bounds__(RB) multi_dot_kernel(const double *__restrict__ V, long ld, int k,
+                                                       const double *__restrict__ w, long n,
+                                                       double *__restrict__ out) {
+    double acc[KCHUNK];
+#pragma unroll
+    for (int j = 0; j < KCHUNK; ++j)
+        acc[j] = 0.0;
+    for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB) {
+        const double wi = w[i];
+#pragma unroll
+        for (int j = 0; j < KCHUNK; ++j)
+            if (j < k)
+                acc[j] = fma(V[j * ld + i], wi, acc[j]);
+    }
+    __shared__ double ws[KCHUNK][RB / 32];
+#pragma unroll
+    for (int j = 0; j < KCHUNK; ++j) {
+        double a = acc[j];
+        for (int o = 16; o > 0; o >>= 1)
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0)
+            ws[j][threadIdx.x >> 5] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < k) {
+        double a = 0.0;
+        for (int q = 0; q < RB / 32; ++q)
+            a += ws[threadIdx.x][q];
+        atomicAdd(out + threadIdx.x, a);
+    }
+}
+
+// x[i] = beta*x[i] + alpha * sum_j s[j] V[j*ld+i]
+__global__ void __launch_bounds__(RB) combine_kernel(const double *__restrict__ V, long ld, int k,
+                                                     const double *__restrict__ s, double alpha, double beta,
+                                                     double *__restrict__ x, long n) {
+    extern __shared__ double sh[];
+    for (int j = threadIdx.x; j < k; j += RB)
+        sh[j] = s[j];
+    __syncthreads();
+    for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB) {
+        double a = 0.0;
+        for (int j = 0; j < k; ++j)
+            a = fma(sh[j], V[j * ld + i], a);
+        x[i] = (beta == 0.0 ? 0.0 : beta * x[i]) + alpha * a;
+    }
+}
+
+// Ritz vector, its image, residual and Davidson correction in one pass:
+//   x = V s, ax = W s, r = ax - theta x, t = r / (theta - d), rnorm2 += |r|^2
+__global__ void __launch_bounds__(RB) ritz_residual_kernel(const double *__restrict__ V, const double *__restrict__ W,
+                                                           long ld, int k, const double *__restrict__ s, double theta,
+                                                           const double *__restrict__ diag, double *__restrict__ x,
+                                                           double *__restrict__ ax, double *__restrict__ t, long n,
+                                                           double *__restrict__ rnorm2) {
+    extern __shared__ double sh[];
+    for (int j = threadIdx.x; j < k; j += RB)
+        sh[j] = s[j];
+    __syncthreads();
+    double acc = 0.0;
+    for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB) {
+        double xv = 0.0, av = 0.0;
+        for (int j = 0; j < k; ++j) {
+            xv = fma(sh[j], V[j * ld + i], xv);
+            av = fma(sh[j], W[j * ld + i], av);
+        }
+        const double r = av - theta * xv;
+        double den = theta - diag[i];
+        if (fabs(den) < 1.0e-8)
+            den = (den < 0.0) ? -1.0e-8 : 1.0e-8;
+        x[i] = xv;
+        ax[i] = av;
+        t[i] = r / den;
+        acc = fma(r, r, acc);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double ws[RB / 32];
+    if ((threadIdx.x & 31) == 0)
+        ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int q = 0; q < RB / 32; ++q)
+            a += ws[q];
+        atomicAdd(rnorm2, a);
+    }
+}
+
+__global__ void scale_kernel(double *x, double alpha, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        x[i] *= alpha;
+}
+
+// deterministic start vector: unit vector at `hot` plus small hash noise so that no symmetry sector
+// of the Hamiltonian is excluded from the search (Spectra starts from a random vector)
+__global__ void guess_kernel(double *v, long row0, long nloc, long nrow, long hot, double eps, u32 seed) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long)gridDim.x * blockDim.x) {
+        const long g = row0 + i;
+        double val = 0.0;
+        if (g < nrow) {
+            const u32 hsh = mix64((u64)g * 0x9e3779b97f4a7c15ULL + seed);
+            val = eps * ((double)hsh * (2.0 / 4294967296.0) - 1.0);
+            if (g == hot)
+                val += 1.0;
+        }
+        v[i] = val;
+    }
+}
+
+// cyclic Jacobi for a dense symmetric m x m matrix (row-major a, destroyed); eigenvalues ascending in w,
+// eigenvectors in the COLUMNS of z (row-major, z[i*m + j] = component i of vector j)
+void jacobi_eigh(std::vector<double> &a, int m, std::vector<double> &w, std::vector<double> &z) {
+    z.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i)
+        z[(size_t)i * m + i] = 1.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0, dsum = 0.0;
+        for (int i = 0; i < m; ++i) {
+            dsum += a[(size_t)i * m + i] * a[(size_t)i * m + i];
+            for (int j = i + 1; j < m; ++j)
+                off += a[(size_t)i * m + j] * a[(size_t)i * m + j];
+        }
+        if (off <= 1.0e-60 || off <= 1.0e-34 * dsum)
+            break;
+        for (int p = 0; p < m - 1; ++p)
+            for (int q = p + 1; q < m; ++q) {
+                const double apq = a[(size_t)p * m + q];
+                if (apq == 0.0)
+                    continue;
+                const double app = a[(size_t)p * m + p], aqq = a[(size_t)q * m + q];
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+                for (int k = 0; k < m; ++k) {
+                    const double akp = a[(size_t)k * m + p], akq = a[(size_t)k * m + q];
+                    a[(size_t)k * m + p] = c * akp - s * akq;
+                    a[(size_t)k * m + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < m; ++k) {
+                    const double apk = a[(size_t)p * m + k], aqk = a[(size_t)q * m + k];
+                    a[(size_t)p * m + k] = c * apk - s * aqk;
+                    a[(size_t)q * m + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < m; ++k) {
+                    const double zkp = z[(size_t)k * m + p], zkq = z[(size_t)k * m + q];
+                    z[(size_t)k * m + p] = c * zkp - s * zkq;
+                    z[(size_t)k * m + q] = s * zkp + c * zkq;
+                }
+            }
+    }
+    std::vector<int> order(m);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return a[(size_t)x * m + x] < a[(size_t)y * m + y]; });
+    w.resize(m);
+    std::vector<double> zs((size_t)m * m);
+    for (int j = 0; j < m; ++j) {
+        w[j] = a[(size_t)order[j] * m + order[j]];
+        for (int i = 0; i < m; ++i)
+            zs[(size_t)i * m + j] = z[(size_t)i * m + order[j]];
+    }
+    z.swap(zs);
+}
+
+struct Solver {
+    pyci_op *op;
+    pyci_ctx *ctx;
+    cudaStream_t st;
+    long nrow, nloc, ld; // ld = npad
+    int R;
+    int grid;
+    double *V = nullptr, *W = nullptr, *X = nullptr, *AX = nullptr, *T = nullptr;
+    double *xfull = nullptr; // all-gather target (R > 1)
+    double *dsmall = nullptr; // device scratch for dots / coefficients
+    double *hsmall = nullptr; // pinned host mirror
+    int small_cap = 0;
+    pyci_solve_stats stats;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+
+    ~Solver() {
+        cudaFree(V);
+        cudaFree(W);
+        cudaFree(X);
+        cudaFree(AX);
+        cudaFree(T);
+        cudaFree(xfull);
+        cudaFree(dsmall);
+        if (hsmall)
+            cudaFreeHost(hsmall);
+        if (e0)
+            cudaEventDestroy(e0);
+        if (e1)
+            cudaEventDestroy(e1);
+    }
+
+    // w = A v   (v, w: local shards)
+    int apply(const double *v, double *w) {
+        PYCI_CUDA(cudaEventRecord(e0, st));
+        const double *xin = v;
+        if (R > 1) {
+            PYCI_TRY(comm_allgather_f64(ctx, v, xfull, ld));
+            xin = xfull;
+        }
+        PYCI_TRY(spmv_launch(op, xin, w));
+        PYCI_CUDA(cudaEventRecord(e1, st));
+        stats.matvecs++;
+        return PYCI_OK;
+    }
+
+    // host[j] = V_j . w for j < k (all-reduced over ranks)
+    int dots(const double *Vb, int k, const double *w, double *host) {
+        for (int j0 = 0; j0 < k; j0 += small_cap) {
+            const int kk = std::min(k - j0, small_cap);
+            PYCI_CUDA(cudaMemsetAsync(dsmall, 0, sizeof(double) * kk, st));
+            for (int c0 = 0; c0 < kk; c0 += KCHUNK) {
+                const int kc = std::min(KCHUNK, kk - c0);
+                multi_dot_kernel<<<grid, RB, 0, st>>>(Vb + (long)(j0 + c0) * ld, ld, kc, w, nloc, dsmall + c0);
+                ctx->launches++;
+            }
+            if (R > 1)
+                PYCI_TRY(comm_allreduce_sum_f64(ctx, dsmall, kk));
+            PYCI_CUDA(cudaMemcpyAsync(hsmall, dsmall, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
+            PYCI_CUDA(cudaStreamSynchronize(st));
+            std::memcpy(host + j0, hsmall, sizeof(double) * kk);
+        }
+        return PYCI_OK;
+    }
+
+    // x = beta x + alpha * sum_j s_j Vb_j
+    int combine(const double *Vb, int k, const double *s_host, double alpha, double beta, double *x) {
+        if (k > small_cap)
+            PYCI_FAIL(PYCI_ERR_RUNTIME, "subspace larger than scratch");
+        std::memcpy(hsmall, s_host, sizeof(double) * k);
+        PYCI_CUDA(cudaMemcpyAsync(dsmall, hsmall, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        combine_kernel<<<grid, RB, sizeof(double) * k, st>>>(Vb, ld, k, dsmall, alpha, beta, x, nloc);
+        ctx->launches++;
+        PYCI_CUDA(cudaStreamSynchronize(st)); // hsmall is reused
+        return PYCI_OK;
+    }
+
+    // orthogonalise t against V[0..m) (classical Gram-Schmidt, twice) and normalise; returns the norm
+    // of the orthogonal component relative to the input norm in *rel
+    int orthonormalize(double *t, int m, std::vector<double> &tmp, double *rel) {
+        double n0 = 0.0;
+        PYCI_TRY(dots(t, 1, t, &n0));
+        if (!(n0 > 0.0)) {
+            *rel = 0.0;
+            return PYCI_OK;
+        }
+        for (int pass = 0; pass < 2 && m > 0; ++pass) {
+            tmp.resize(m);
+            PYCI_TRY(dots(V, m, t, tmp.data()));
+            PYCI_TRY(combine(V, m, tmp.data(), -1.0, 1.0, t));
+        }
+        double n1 = 0.0;
+        PYCI_TRY(dots(t, 1, t, &n1));
+        *rel = std::sqrt(n1 / n0);
+        if (n1 > 0.0) {
+            scale_kernel<<<grid, RB, 0, st>>>(t, 1.0 / std::sqrt(n1), nloc);
+            ctx->launches++;
+        }
+        return PYCI_OK;
+    }
+};
+
+} // namespace
+
+int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, double tol, double *evals,
+               double *evecs, pyci_solve_stats *stats_out) {
+    pyci_ctx *ctx = op->ctx;
+    const long nrow = op->nrow;
+    const int R = ctx->nranks;
+    if (ncv == -1)
+        ncv = std::min(nrow, std::max(2 * n + 1, 20L));
+    if (maxiter == -1)
+        maxiter = n * nrow * 10;
+    if (ncv <= n || ncv > nrow)
+        PYCI_FAIL(PYCI_ERR_VALUE, "ncv must satisfy n < ncv <= nrow (n=%ld, ncv=%ld, nrow=%ld)", n, ncv, nrow);
+    // Davidson needs room for the n Ritz vectors plus at least one correction per root
+    const int mmax = (int)std::min<long>(nrow, std::max<long>(ncv, 2 * n));
+    const int nroot = (int)n;
+
+    Solver S;
+    S.op = op;
+    S.ctx = ctx;
+    S.st = ctx->stream;
+    S.nrow = nrow;
+    S.nloc = op->nloc;
+    S.ld = op->npad;
+    S.R = R;
+    S.grid = (int)std::max<long>(1, std::min<long>((S.nloc + RB - 1) / RB, (long)ctx->sm_count * 8));
+    S.small_cap = std::max(mmax + nroot, 64);
+    std::memset(&S.stats, 0, sizeof(S.stats));
+    const size_t vec = sizeof(double) * (size_t)S.ld;
+    PYCI_CUDA(cudaMalloc(&S.V, vec * mmax));
+    PYCI_CUDA(cudaMalloc(&S.W, vec * mmax));
+    PYCI_CUDA(cudaMalloc(&S.X, vec * nroot));
+    PYCI_CUDA(cudaMalloc(&S.AX, vec * nroot));
+    PYCI_CUDA(cudaMalloc(&S.T, vec * nroot));
+    PYCI_CUDA(cudaMemsetAsync(S.V, 0, vec * mmax, S.st));
+    PYCI_CUDA(cudaMemsetAsync(S.W, 0, vec * mmax, S.st));
+    PYCI_CUDA(cudaMemsetAsync(S.X, 0, vec * nroot, S.st));
+    PYCI_CUDA(cudaMemsetAsync(S.AX, 0, vec * nroot, S.st));
+    PYCI_CUDA(cudaMemsetAsync(S.T, 0, vec * nroot, S.st));
+    PYCI_CUDA(cudaMalloc(&S.xfull, vec * R));
+    PYCI_CUDA(cudaMalloc(&S.dsmall, sizeof(double) * S.small_cap));
+    PYCI_CUDA(cudaMallocHost(&S.hsmall, sizeof(double) * S.small_cap));
+    PYCI_CUDA(cudaEventCreate(&S.e0));
+    PYCI_CUDA(cudaEventCreate(&S.e1));
+    cudaEvent_t t_begin, t_end;
+    PYCI_CUDA(cudaEventCreate(&t_begin));
+    PYCI_CUDA(cudaEventCreate(&t_end));
+    PYCI_CUDA(cudaEventRecord(t_begin, S.st));
+
+    // ---- start vectors
+    std::vector<double> hdiag((size_t)S.ld * R);
+    {
+        const double *dsrc = op->diag;
+        if (R > 1) {
+            PYCI_TRY(comm_allgather_f64(ctx, op->diag, S.xfull, S.ld));
+            dsrc = S.xfull;
+        }
+        PYCI_CUDA(cudaMemcpyAsync(hdiag.data(), dsrc, vec * R, cudaMemcpyDeviceToHost, S.st));
+        PYCI_CUDA(cudaStreamSynchronize(S.st));
+    }
+    std::vector<long> order(nrow);
+    std::iota(order.begin(), order.end(), 0L);
+    const long nguess = std::min<long>(nrow, nroot);
+    std::partial_sort(order.begin(), order.begin() + nguess, order.end(), [&](long a, long b) {
+        return hdiag[a] < hdiag[b] || (hdiag[a] == hdiag[b] && a < b);
+    });
+
+    int m = 0; // subspace dimension
+    std::vector<double> tmp;
+    for (int j = 0; j < nroot; ++j) {
+        double *t = S.T;
+        if (j == 0 && c0 != nullptr) {
+            PYCI_CUDA(cudaMemsetAsync(t, 0, vec, S.st));
+            PYCI_CUDA(cudaMemcpyAsync(t, c0 + op->row0, sizeof(double) * S.nloc, cudaMemcpyHostToDevice, S.st));
+        } else {
+            guess_kernel<<<S.grid, RB, 0, S.st>>>(t, op->row0, S.nloc, nrow, order[j], 1.0e-3, 0x5eedu + 77u * j);
+            ctx->launches++;
+        }
+        double rel = 0.0;
+        PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
+        if (rel < 1.0e-12) { // degenerate start vector (e.g. c0 == 0): fall back to the unit-vector guess
+            guess_kernel<<<S.grid, RB, 0, S.st>>>(t, op->row0, S.nloc, nrow, order[j], 1.0e-3, 0xabcdu + 131u * j);
+            ctx->launches++;
+            PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
+        }
+        PYCI_CUDA(cudaMemcpyAsync(S.V + (size_t)m * S.ld, t, vec, cudaMemcpyDeviceToDevice, S.st));
+        ++m;
+    }
+    int nnew = m;
+
+    std::vector<double> G((size_t)mmax * mmax, 0.0); // projected matrix V^T A V (row-major, leading dim mmax)
+    std::vector<double> theta, Z, Gw, col(mmax);
+    std::vector<double> rn(nroot, 0.0);
+    std::vector<char> conv(nroot, 0);
+    const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+    bool done = false;
+    double spmv_ms = 0.0;
+    long iter = 0;
+    for (; iter < maxiter; ++iter) {
+        // images of the new basis vectors and the new rows/columns of G
+        for (int j = m - nnew; j < m; ++j) {
+            PYCI_TRY(S.apply(S.V + (size_t)j * S.ld, S.W + (size_t)j * S.ld));
+            PYCI_TRY(S.dots(S.V, m, S.W + (size_t)j * S.ld, col.data()));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, S.e0, S.e1);
+            spmv_ms += ms;
+            for (int i = 0; i < m; ++i)
+                G[(size_t)i * mmax + j] = G[(size_t)j * mmax + i] = col[i];
+        }
+        // Rayleigh-Ritz
+        Gw.assign((size_t)m * m, 0.0);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j)
+                Gw[(size_t)i * m + j] = 0.5 * (G[(size_t)i * mmax + j] + G[(size_t)j * mmax + i]);
+        jacobi_eigh(Gw, m, theta, Z);
+        // residuals and corrections
+        const int nr = std::min(nroot, m);
+        PYCI_CUDA(cudaMemsetAsync(S.dsmall + S.small_cap - nroot, 0, sizeof(double) * nroot, S.st));
+        std::vector<double> sj(m);
+        for (int r = 0; r < nr; ++r) {
+            for (int i = 0; i < m; ++i)
+                sj[i] = Z[(size_t)i * m + r];
+            std::memcpy(S.hsmall, sj.data(), sizeof(double) * m);
+            PYCI_CUDA(cudaMemcpyAsync(S.dsmall, S.hsmall, sizeof(double) * m, cudaMemcpyHostToDevice, S.st));
+            ritz_residual_kernel<<<S.grid, RB, sizeof(double) * m, S.st>>>(
+                S.V, S.W, S.ld, m, S.dsmall, theta[r], op->diag, S.X + (size_t)r * S.ld, S.AX + (size_t)r * S.ld,
+                S.T + (size_t)r * S.ld, S.nloc, S.dsmall + S.small_cap - nroot + r);
+            ctx->launches++;
+            PYCI_CUDA(cudaStreamSynchronize(S.st));
+        }
+        if (R > 1)
+            PYCI_TRY(comm_allreduce_sum_f64(ctx, S.dsmall + S.small_cap - nroot, nroot));
+        PYCI_CUDA(cudaMemcpyAsync(S.hsmall, S.dsmall + S.small_cap - nroot, sizeof(double) * nroot,
+                                  cudaMemcpyDeviceToHost, S.st));
+        PYCI_CUDA(cudaStreamSynchronize(S.st));
+        bool all = (nr == nroot);
+        double worst = 0.0;
+        for (int r = 0; r < nr; ++r) {
+            rn[r] = std::sqrt(std::max(S.hsmall[r], 0.0));
+            conv[r] = rn[r] <= tol * std::max(eps23, std::fabs(theta[r]));
+            all = all && conv[r];
+            worst = std::max(worst, rn[r]);
+        }
+        S.stats.residual = worst;
+        S.stats.iterations = iter + 1;
+        if (all || m == nrow) {
+            // m == nrow: the subspace is the whole space, the Ritz pairs are exact
+            done = (nr == nroot);
+            break;
+        }
+        // restart when the corrections would not fit
+        int nunconv = 0;
+        for (int r = 0; r < nr; ++r)
+            nunconv += !conv[r];
+        if (m + nunconv > mmax) {
+            PYCI_CUDA(cudaMemcpyAsync(S.V, S.X, vec * nr, cudaMemcpyDeviceToDevice, S.st));
+            PYCI_CUDA(cudaMemcpyAsync(S.W, S.AX, vec * nr, cudaMemcpyDeviceToDevice, S.st));
+            std::fill(G.begin(), G.end(), 0.0);
+            for (int r = 0; r < nr; ++r)
+                G[(size_t)r * mmax + r] = theta[r];
+            m = nr;
+            S.stats.restarts++;
+        }
+        // expand
+        nnew = 0;
+        for (int r = 0; r < nr && m < mmax; ++r) {
+            if (conv[r])
+                continue;
+            double *t = S.T + (size_t)r * S.ld;
+            double rel = 0.0;
+            PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
+            if (rel < 1.0e-10)
+                continue; // correction already in the subspace
+            PYCI_CUDA(cudaMemcpyAsync(S.V + (size_t)m * S.ld, t, vec, cudaMemcpyDeviceToDevice, S.st));
+            ++m;
+            ++nnew;
+        }
+        if (nnew == 0) {
+            // cannot expand: add a fresh pseudo-random direction to escape stagnation
+            double *t = S.T;
+            guess_kernel<<<S.grid, RB, 0, S.st>>>(t, op->row0, S.nloc, nrow, -1, 1.0, 0x1234u + (u32)iter);
+            ctx->launches++;
+            double rel = 0.0;
+            PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
+            if (rel < 1.0e-10 || m >= mmax)
+                break;
+            PYCI_CUDA(cudaMemcpyAsync(S.V + (size_t)m * S.ld, t, vec, cudaMemcpyDeviceToDevice, S.st));
+            ++m;
+            nnew = 1;
+        }
+    }
+    PYCI_CUDA(cudaEventRecord(t_end, S.st));
+    PYCI_CUDA(cudaStreamSynchronize(S.st));
+    float total_ms = 0;
+    cudaEventElapsedTime(&total_ms, t_begin, t_end);
+    cudaEventDestroy(t_begin);
+    cudaEventDestroy(t_end);
+    S.stats.seconds = total_ms * 1e-3;
+    S.stats.spmv_seconds = spmv_ms * 1e-3;
+    if (stats_out)
+        *stats_out = S.stats;
+    if (!done)
+        PYCI_FAIL(PYCI_ERR_RUNTIME, "did not converge");
+
+    // results: evals (+ecore, sparseop.cpp:140-141), evecs[n][nrow] row-major (:142-144)
+    for (int r = 0; r < nroot; ++r)
+        evals[r] = theta[r] + op->ecore;
+    for (int r = 0; r < nroot; ++r) {
+        const double *src = S.X + (size_t)r * S.ld;
+        if (R > 1) {
+            PYCI_TRY(comm_allgather_f64(ctx, src, S.xfull, S.ld));
+            src = S.xfull;
+        }
+        PYCI_CUDA(cudaMemcpyAsync(evecs + (size_t)r * nrow, src, sizeof(double) * nrow, cudaMemcpyDeviceToHost, S.st));
+    }
+    PYCI_CUDA(cudaStreamSynchronize(S.st));
+    return PYCI_OK;
+}

@@ -1,0 +1,323 @@
+"""Parity of the sm_100a path (through pyci_b200._pyci -> C ABI -> CUDA kernels) with the golden vectors of
+the compiled reference and with the CPU oracle.  Bars (BASELINE.json north_star): indptr/indices bit-exact,
+matrix elements <= 1e-12 relative (they are in fact bit-identical), eigenvalues <= 1e-10 Eh."""
+import numpy as np
+import pytest
+
+from conftest import datafile, seeded_vec, sha
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DATA_RTOL = 1e-12   # matrix elements, relative to the largest |element| of the operator
+E_ATOL = 1e-10      # eigenvalues, Hartree
+
+SMALL = [("h4_sto3g", "fullci", (2, 2)), ("lih_sto6g", "fullci", (2, 2)), ("BH_sto-3g_eq", "fullci", (3, 3)),
+         ("h6_sto_3g", "fullci", (4, 2)), ("be_ccpvdz", "doci", (2, 2)), ("h2_sto3g", "fullci", (1, 1))]
+KIND = {"doci": O.DOCI, "fullci": O.FULLCI, "genci": O.GENCI}
+
+
+@pytest.fixture(scope="module")
+def pyci():
+    import pyci_b200
+    assert pyci_b200.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return pyci_b200
+
+
+def make(pyci, fn, kind, occ):
+    ham = pyci.hamiltonian(datafile(fn))
+    wfn = getattr(pyci, kind + "_wfn")(ham.nbasis, *occ)
+    wfn.add_all_dets()
+    return ham, wfn
+
+
+def assert_csr(op, indptr, indices, data):
+    assert op.indptr().dtype == np.int64 and op.indices().dtype == np.int64 and op.data().dtype == np.float64
+    assert np.array_equal(op.indptr(), indptr)
+    assert np.array_equal(op.indices(), indices)
+    assert op.size == len(indices)
+    if len(data):
+        assert np.max(np.abs(op.data() - data)) <= DATA_RTOL * np.max(np.abs(data))
+
+
+@pytest.mark.parametrize("fn,kind,occ", SMALL)
+def test_small_csr_matvec_energy(pyci, small, fn, kind, occ):
+    ham, wfn = make(pyci, fn, kind, occ)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    assert np.array_equal(wfn.to_det_array(), small[tag + ".dets"])
+    x = seeded_vec(len(wfn), 11)
+    for name, kw in (("sym", dict(symmetric=True)), ("nonsym", dict(symmetric=False)),
+                     ("rect", dict(nrow=len(wfn) - 10, symmetric=False))):
+        if f"{tag}.{name}.indptr" not in small:
+            continue
+        op = pyci.sparse_op(ham, wfn, **kw)
+        assert_csr(op, small[f"{tag}.{name}.indptr"], small[f"{tag}.{name}.indices"], small[f"{tag}.{name}.data"])
+        assert np.array_equal(op.data(), small[f"{tag}.{name}.data"])  # bit-identical in practice
+        y = op(x)
+        ref = small[f"{tag}.{name}.y"]
+        assert y.shape == ref.shape
+        np.testing.assert_allclose(y, ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()))
+    op = pyci.sparse_op(ham, wfn)
+    if len(wfn) > 1:
+        es, cs = op.solve(n=1, tol=1e-10)
+        assert abs(es[0] - float(small[tag + ".E0"])) <= E_ATOL
+        assert cs.shape == (1, len(wfn))
+        r = op(cs[0]) - (es[0] - ham.ecore) * cs[0]
+        assert np.linalg.norm(r) < 1e-7
+
+
+@pytest.mark.parametrize("fn,kind,occ,pinned", [
+    ("be_ccpvdz", "fullci", (2, 2), -14.617409507),   # BASELINE config 1 (test_routines.py:44)
+    ("h2o_ccpvdz", "doci", (5, 5), -75.634588422),    # BASELINE config 2 (test_routines.py:45)
+    ("li2_ccpvdz", "doci", (3, 3), -14.878455349),    # test_routines.py:41
+])
+def test_configs_digest_and_energy(pyci, digests, fn, kind, occ, pinned):
+    ham, wfn = make(pyci, fn, kind, occ)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    g = digests[tag + ".sym"]
+    assert len(wfn) == g["ndet"]
+    op = pyci.sparse_op(ham, wfn)
+    assert op.size == g["nnz"] and op.shape == (g["ndet"], g["ndet"])
+    assert (sha(op.indptr()), sha(op.indices())) == (g["indptr"], g["indices"])
+    assert sha(op.data()) == g["data"]        # values bit-identical to the reference
+    x = seeded_vec(len(wfn), 11)
+    assert abs(np.linalg.norm(op(x)) - g["y_norm"]) <= 1e-11 * g["y_norm"]
+    # the reference's own test call: solve(n=1, ncv=30, tol=1e-6), atol 1e-9 (test_routines.py:53-54)
+    es, cs = op.solve(n=1, ncv=30, tol=1.0e-6)
+    assert abs(es[0] - pinned) <= 1e-9
+    es, cs = op.solve(n=1, tol=1.0e-10)
+    assert abs(es[0] - g["E0"]) <= E_ATOL
+    gn = digests[tag + ".nonsym"]
+    opn = pyci.sparse_op(ham, wfn, symmetric=False)
+    assert (opn.size, sha(opn.indptr()), sha(opn.indices()), sha(opn.data())) == \
+        (gn["nnz"], gn["indptr"], gn["indices"], gn["data"])
+    assert abs(np.linalg.norm(opn(x)) - gn["y_norm"]) <= 1e-11 * gn["y_norm"]
+    # RDMs (atomics: order of accumulation differs, compare numerically)
+    c = seeded_vec(len(wfn), 12)
+    c /= np.linalg.norm(c)
+    r1, r2 = pyci.compute_rdms(wfn, c)
+    gr = digests[tag + ".rdm"]
+    assert abs(r1.sum() - gr["rdm1_sum"]) < 1e-10 and abs(np.abs(r2).sum() - gr["rdm2_abs_sum"]) < 1e-9
+    o1, o2 = O.compute_rdms(KIND[kind], ham.nbasis, occ[0], occ[1], wfn.to_det_array(), c)
+    np.testing.assert_allclose(r1, o1, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(r2, o2, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,occ", [(10, (4, 4)), (9, (4, 3))])
+def test_synthetic_fullci_digest(pyci, digests, n, occ):
+    ecore, one, two = O.synthetic_integrals(n, 1234)
+    ham = pyci.hamiltonian(ecore, one, two)
+    wfn = pyci.fullci_wfn(n, *occ)
+    wfn.add_all_dets()
+    tag = f"syn{n}.fullci{occ[0]}{occ[1]}"
+    for name, sym in (("sym", True), ("nonsym", False)):
+        g = digests[f"{tag}.{name}"]
+        op = pyci.sparse_op(ham, wfn, symmetric=sym)
+        assert (op.size, sha(op.indptr()), sha(op.indices()), sha(op.data())) == \
+            (g["nnz"], g["indptr"], g["indices"], g["data"])
+        if sym:
+            es, _ = op.solve(n=1, tol=1e-10)
+            assert abs(es[0] - g["E0"]) <= E_ATOL
+
+
+def test_selected_space_and_rdms(pyci, small):
+    ecore, one, two = O.synthetic_integrals(8, 1234)
+    ham = pyci.hamiltonian(ecore, one, two)
+    dets = small["syn8.fullci32.sel.dets"]
+    wfn = pyci.fullci_wfn(8, 3, 2, dets)
+    for name, sym in (("sym", True), ("nonsym", False)):
+        op = pyci.sparse_op(ham, wfn, symmetric=sym)
+        assert_csr(op, small[f"syn8.fullci32.sel.{name}.indptr"], small[f"syn8.fullci32.sel.{name}.indices"],
+                   small[f"syn8.fullci32.sel.{name}.data"])
+    c = seeded_vec(len(wfn), 12)
+    c /= np.linalg.norm(c)
+    r1, r2 = pyci.compute_rdms(wfn, c)
+    np.testing.assert_allclose(r1, small["syn8.fullci32.sel.rdm1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(r2, small["syn8.fullci32.sel.rdm2"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("fn,kind,occ", SMALL)
+def test_small_rdms(pyci, small, fn, kind, occ):
+    ham, wfn = make(pyci, fn, kind, occ)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    c = seeded_vec(len(wfn), 12)
+    c /= np.linalg.norm(c)
+    r1, r2 = pyci.compute_rdms(wfn, c)
+    assert r1.shape == small[tag + ".rdm1"].shape and r2.shape == small[tag + ".rdm2"].shape
+    np.testing.assert_allclose(r1, small[tag + ".rdm1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(r2, small[tag + ".rdm2"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("fn,occ", [("h4_sto3g", (2, 2)), ("BH_sto-3g_eq", (3, 3)), ("h6_sto_3g", (4, 2))])
+def test_genci(pyci, genci_golden, fn, occ):
+    """GenCI equals (i) the reference compiled with the two loop bounds fixed and (ii) FullCI on the spatial
+    integrals; its RDMs equal the spin-expanded FullCI RDMs."""
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    n = one.shape[0]
+    h2, g2 = O.spin_orbital_integrals(one, two)
+    tag = f"{fn}.genci{sum(occ)}"
+    gd = genci_golden[tag + ".dets"]
+    hamg = pyci.hamiltonian(ecore, h2, g2)
+    wg = pyci.genci_wfn(2 * n, sum(occ), 0, gd)
+    fw = pyci.fullci_wfn(n, *occ)
+    fw.add_all_dets()
+    assert np.array_equal(pyci.genci_wfn(fw).to_det_array(), gd)
+    hamf = pyci.hamiltonian(ecore, one, two)
+    for name, sym in (("sym", True), ("nonsym", False)):
+        op = pyci.sparse_op(hamg, wg, symmetric=sym)
+        assert_csr(op, genci_golden[f"{tag}.{name}.indptr"], genci_golden[f"{tag}.{name}.indices"],
+                   genci_golden[f"{tag}.{name}.data"])
+        opf = pyci.sparse_op(hamf, fw, symmetric=sym)
+        assert np.array_equal(op.indptr(), opf.indptr()) and np.array_equal(op.indices(), opf.indices())
+        assert np.array_equal(op.data(), opf.data())
+    es, cs = pyci.sparse_op(hamg, wg).solve(n=1, tol=1e-10)
+    esf, csf = pyci.sparse_op(hamf, fw).solve(n=1, tol=1e-10)
+    assert abs(es[0] - esf[0]) <= E_ATOL
+    c = seeded_vec(len(fw), 2)
+    c /= np.linalg.norm(c)
+    s1, s2 = pyci.spinize_rdms(*pyci.compute_rdms(fw, c))
+    g1, g2r = pyci.compute_rdms(wg, c)
+    np.testing.assert_allclose(g1, s1, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(g2r, s2, rtol=0, atol=1e-13)
+
+
+def test_rdm_energy_identity(pyci):
+    """test_routines.py:83-133 restated: traces, DOCI energy from reduced integrals, spin-orbital identity."""
+    for fn, kind, occ in (("be_ccpvdz", "doci", (2, 2)), ("h2o_ccpvdz", "doci", (5, 5)), ("lih_sto6g", "fullci", (2, 2))):
+        ham, wfn = make(pyci, fn, kind, occ)
+        op = pyci.sparse_op(ham, wfn)
+        es, cs = op.solve(n=1, ncv=30, tol=1.0e-6)
+        d1, d2 = pyci.compute_rdms(wfn, cs[0])
+        if kind == "doci":
+            assert abs(np.trace(d1) - wfn.nocc_up) < 1e-9
+            assert abs(np.sum(d2) - wfn.nocc_up * (wfn.nocc_up - 1)) < 1e-9
+            k0, k2 = pyci.reduce_senzero_integrals(ham.h, ham.v, ham.w, wfn.nocc_up)
+            e = ham.ecore + np.einsum("ij,ij", k0, d1) + np.einsum("ij,ij", k2, d2)
+            assert abs(e - es[0]) < 1e-9
+        rdm1, rdm2 = pyci.spinize_rdms(d1, d2)
+        _, one, two = O.read_fcidump(datafile(fn))
+        h2, g2 = O.spin_orbital_integrals(one, two)
+        anti = g2 - g2.transpose(0, 1, 3, 2)
+        e = ham.ecore + np.einsum("ij,ij", h2, rdm1) + 0.25 * np.einsum("ijkl,ijkl", anti, rdm2)
+        assert abs(e - es[0]) < 1e-9
+        assert np.all(np.abs(rdm1 - rdm1.T) < 1e-9)
+
+
+def test_rectangular_like_reference(pyci):
+    """test_routines.py:57-80: excitation-selected space, nrow = len-10, symmetric=False, op(ones) equals the
+    row sums of get_element."""
+    ham = pyci.hamiltonian(datafile("be_ccpvdz"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 2, 2)
+    pyci.add_excitations(wfn, 0, 1, 2)
+    nrow = len(wfn) - 10
+    op = pyci.sparse_op(ham, wfn, nrow, symmetric=False)
+    assert op.shape == (nrow, len(wfn))
+    y = op(np.ones(op.shape[1], dtype=pyci.c_double))
+    assert y.ndim == 1 and y.shape[0] == nrow
+    ip, ix, dv = op.indptr(), op.indices(), op.data()
+    z = np.add.reduceat(dv, ip[:-1])
+    np.testing.assert_allclose(y, z, rtol=0, atol=1e-11)
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, nrow, 5):
+        row = dict(zip(ix[ip[i]:ip[i + 1]].tolist(), dv[ip[i]:ip[i + 1]].tolist()))
+        for j in list(row)[:4] + rng.integers(0, len(wfn), 4).tolist():
+            assert op.get_element(int(i), int(j)) == row.get(int(j), 0.0)
+    dets = wfn.to_det_array()
+    oi, ox, od = O.sparse_op(O.FULLCI, ham.nbasis, 2, 2, dets, (ham.one_mo, ham.two_mo), nrow=nrow, symmetric=False)
+    assert_csr(op, oi, ox, od)
+
+
+def test_update_after_adding_determinants(pyci):
+    """HCI-style growth (sparseop.cpp:175-178): update(ham, wfn) after appending determinants gives the same
+    operator as a fresh build."""
+    ham = pyci.hamiltonian(datafile("lih_sto6g"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 2, 2)
+    pyci.add_excitations(wfn, 0, 1)
+    op = pyci.sparse_op(ham, wfn)
+    n0 = op.shape[0]
+    pyci.add_excitations(wfn, 2)
+    assert len(wfn) > n0
+    op.update(ham, wfn)
+    fresh = pyci.sparse_op(ham, wfn)
+    assert op.shape == fresh.shape == (len(wfn), len(wfn))
+    assert np.array_equal(op.indptr(), fresh.indptr()) and np.array_equal(op.indices(), fresh.indices())
+    assert np.array_equal(op.data(), fresh.data())
+    oi, ox, od = O.sparse_op(O.FULLCI, ham.nbasis, 2, 2, wfn.to_det_array(), (ham.one_mo, ham.two_mo))
+    assert_csr(op, oi, ox, od)
+
+
+def test_solve_guards_and_edge_cases(pyci):
+    ham = pyci.hamiltonian(datafile("h2_sto3g"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 1, 1)
+    wfn.add_all_dets()
+    op = pyci.sparse_op(ham, wfn)
+    with pytest.raises(ValueError):          # sparseop.cpp:116-117
+        op.solve(n=len(wfn))
+    rect = pyci.sparse_op(ham, wfn, len(wfn) - 1, symmetric=False)
+    with pytest.raises(TypeError):           # sparseop.cpp:118-119
+        rect.solve(n=1)
+    es, cs = op.solve(n=len(wfn) - 1, tol=1e-10)     # several roots (test_odometer.py style)
+    ip, ix, dv = O.sparse_op(O.FULLCI, ham.nbasis, 1, 1, wfn.to_det_array(), (ham.one_mo, ham.two_mo))
+    w = np.linalg.eigvalsh(O.full_symmetric(ip, ix, dv, len(wfn)).toarray()) + ham.ecore
+    np.testing.assert_allclose(np.sort(es), w[:len(es)], rtol=0, atol=1e-9)
+    # single determinant: E = H00 + ecore, c = [1]  (sparseop.cpp:120-124)
+    one = pyci.fullci_wfn(ham.nbasis, 1, 1)
+    one.add_hartreefock_det()
+    op1 = pyci.sparse_op(ham, one)
+    es, cs = op1.solve()
+    assert es.shape == (1,) and cs.shape == (1, 1) and cs[0, 0] == 1.0
+    assert es[0] == op1.get_element(0, 0) + ham.ecore
+    # start vector
+    ham = pyci.hamiltonian(datafile("lih_sto6g"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 2, 2)
+    wfn.add_all_dets()
+    op = pyci.sparse_op(ham, wfn)
+    e_ref, _ = op.solve(n=1, tol=1e-10)
+    c0 = np.zeros(len(wfn))
+    c0[0] = 1.0
+    e_c0, _ = op.solve(n=1, c0=c0, tol=1e-10)
+    assert abs(e_ref[0] - e_c0[0]) <= E_ATOL
+    e3, c3 = op.solve(n=3, tol=1e-9)
+    ip, ix, dv = O.sparse_op(O.FULLCI, ham.nbasis, 2, 2, wfn.to_det_array(), (ham.one_mo, ham.two_mo))
+    w = np.linalg.eigvalsh(O.full_symmetric(ip, ix, dv, len(wfn)).toarray()) + ham.ecore
+    np.testing.assert_allclose(e3, w[:3], rtol=0, atol=1e-9)
+
+
+def test_unsupported_and_invalid_inputs_fail_loudly(pyci):
+    ecore, one, two = O.synthetic_integrals(66, 7)
+    ham = pyci.hamiltonian(ecore, one, two)
+    wfn = pyci.doci_wfn(66, 2, 2)
+    wfn.add_all_dets()
+    with pytest.raises(RuntimeError):        # nbasis > 64: no device path and no CPU fallback
+        pyci.sparse_op(ham, wfn)
+    ham = pyci.hamiltonian(datafile("h4_sto3g"))
+    dets = np.array([[3, 3], [3, 3]], dtype=np.uint64)  # duplicate determinant
+    with pytest.raises(ValueError):
+        pyci.sparse_op(ham, pyci.fullci_wfn(4, 2, 2, dets))
+
+
+def test_key_modes(pyci):
+    """64-bit keys (FullCI 16 < nbasis <= 32) and 128-bit keys (nbasis > 32); GenCI 64-bit (nbasis > 32)."""
+    for n, occ in ((20, (2, 1)), (40, (1, 1))):
+        ecore, one, two = O.synthetic_integrals(n, 3)
+        ham = pyci.hamiltonian(ecore, one, two)
+        wfn = pyci.fullci_wfn(n, *occ)
+        wfn.add_all_dets()
+        op = pyci.sparse_op(ham, wfn)
+        oi, ox, od = O.sparse_op(O.FULLCI, n, occ[0], occ[1], wfn.to_det_array(), (one, two))
+        assert_csr(op, oi, ox, od)
+        assert np.array_equal(op.data(), od)
+    n = 36
+    ecore, one, two = O.synthetic_integrals(n, 4)
+    ham = pyci.hamiltonian(ecore, one, two)
+    wfn = pyci.genci_wfn(n, 2, 0)
+    pyci.add_excitations(wfn, 0, 1, 2)
+    op = pyci.sparse_op(ham, wfn, symmetric=False)
+    oi, ox, od = O.sparse_op(O.GENCI, n, 2, 0, wfn.to_det_array(), (one, two), symmetric=False)
+    assert_csr(op, oi, ox, od)
+    wfn = pyci.doci_wfn(40, 2, 2)
+    wfn.add_all_dets()
+    op = pyci.sparse_op(pyci.hamiltonian(*O.synthetic_integrals(40, 5)), wfn)
+    _, one, two = O.synthetic_integrals(40, 5)
+    oi, ox, od = O.sparse_op(O.DOCI, 40, 2, 2, wfn.to_det_array(), O.senzero_integrals(one, two))
+    assert_csr(op, oi, ox, od)
