@@ -89,6 +89,11 @@ PYCI_API void pyci_ham_destroy(pyci_ham *ham);
 PYCI_API int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
                     const uint64_t *dets, pyci_wfn **out);
 PYCI_API void pyci_wfn_destroy(pyci_wfn *wfn);
+/* Rebuild the hash index from the determinants already resident in HBM (what SparseOp::update's
+ * callers get from Wfn::add_det, onespinwfn.cpp:141-149: the index is part of the construction path).
+ * pyci_wfn_index_seconds: device seconds of the last index build. */
+PYCI_API int pyci_wfn_reindex(pyci_wfn *wfn);
+PYCI_API double pyci_wfn_index_seconds(const pyci_wfn *wfn);
 /* index_det for a batch of determinants (same layout as dets); out[i] = row index or -1 */
 PYCI_API int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out);
 

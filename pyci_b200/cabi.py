@@ -1,0 +1,250 @@
+r"""ctypes view of the C ABI of ``libpyci_b200.so`` (``include/pyci_b200.h``).
+
+This is the binding a maintainer of the reference would write to reach the B200 path without pybind11
+(INTEGRATION.md shows the same calls from C++).  ``bench.py`` and the ``-m gpu`` tests use it to drive the
+library with device-resident inputs; ``tests/test_abi.py`` uses :data:`PROTOTYPES` to check that every
+function the header declares is exported.  Loading the library needs no GPU; every compute entry point
+fails with ``PYCI_ERR_CUDA`` when no device is visible (there is no CPU fallback).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY = os.path.join(_HERE, "libpyci_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "pyci_b200.h")
+
+OK, ERR_VALUE, ERR_TYPE, ERR_RUNTIME, ERR_CUDA, ERR_MEMORY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+DOCI, FULLCI, GENCI = 0, 1, 2
+
+_vp, _i, _l, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_double
+_vpp = ctypes.POINTER(ctypes.c_void_p)
+
+
+class SolveStats(ctypes.Structure):
+    _fields_ = [("matvecs", _l), ("iterations", _l), ("restarts", _l), ("residual", _d), ("seconds", _d),
+                ("spmv_seconds", _d)]
+
+
+# name -> (restype, argtypes); one entry per PYCI_API function of include/pyci_b200.h
+PROTOTYPES = {
+    "pyci_last_error": (ctypes.c_char_p, []),
+    "pyci_abi_version": (_i, []),
+    "pyci_device_count": (_i, []),
+    "pyci_ctx_create": (_i, [_i, _vp, _vpp]),
+    "pyci_ctx_destroy": (None, [_vp]),
+    "pyci_ctx_synchronize": (_i, [_vp]),
+    "pyci_nccl_unique_id": (_i, [_vp]),
+    "pyci_ctx_init_comm": (_i, [_vp, _i, _i, _vp]),
+    "pyci_ctx_rank": (_i, [_vp]),
+    "pyci_ctx_nranks": (_i, [_vp]),
+    "pyci_ctx_launch_count": (_l, [_vp]),
+    "pyci_ctx_reset_launch_count": (None, [_vp]),
+    "pyci_ham_upload": (_i, [_vp, _l, _d, _vp, _vp, _vp, _vp, _vp, _vpp]),
+    "pyci_ham_destroy": (None, [_vp]),
+    "pyci_wfn_upload": (_i, [_vp, _i, _l, _l, _l, _l, _vp, _vpp]),
+    "pyci_wfn_destroy": (None, [_vp]),
+    "pyci_wfn_reindex": (_i, [_vp]),
+    "pyci_wfn_index_seconds": (_d, [_vp]),
+    "pyci_wfn_index_dets": (_i, [_vp, _l, _vp, _vp]),
+    "pyci_op_build": (_i, [_vp, _vp, _vp, _l, _l, _i, _vpp]),
+    "pyci_op_destroy": (None, [_vp]),
+    "pyci_op_nrow": (_l, [_vp]),
+    "pyci_op_ncol": (_l, [_vp]),
+    "pyci_op_row_begin": (_l, [_vp]),
+    "pyci_op_row_count": (_l, [_vp]),
+    "pyci_op_size": (_l, [_vp]),
+    "pyci_op_stored_nnz": (_l, [_vp]),
+    "pyci_op_ecore": (_d, [_vp]),
+    "pyci_op_build_times": (_i, [_vp, _vp]),
+    "pyci_op_export_csr": (_i, [_vp, _vp, _vp, _vp]),
+    "pyci_op_matvec": (_i, [_vp, _vp, _vp]),
+    "pyci_op_matvec_dev": (_i, [_vp, _vp, _vp]),
+    "pyci_op_time_spmv": (_i, [_vp, _i, _i, _l, _vp]),
+    "pyci_op_get_element": (_i, [_vp, _l, _l, _vp]),
+    "pyci_op_solve": (_i, [_vp, _l, _vp, _l, _l, _d, _vp, _vp, ctypes.POINTER(SolveStats)]),
+    "pyci_compute_rdms": (_i, [_vp, _vp, _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+class PyciError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("pyci_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+def lib():
+    """Load ``libpyci_b200.so`` (once) and attach the prototypes.  Raises OSError if it is not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIBRARY):
+            raise OSError("%s is not built: run `make -C %s`" % (LIBRARY, os.path.join(_HERE, "csrc")))
+        L = ctypes.CDLL(LIBRARY, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(status):
+    if status != OK:
+        raise PyciError(status, lib().pyci_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """pyci_ctx: one device + stream (+ NCCL communicator)."""
+
+    def __init__(self, device=0, stream=0):
+        self.handle = ctypes.c_void_p()
+        check(lib().pyci_ctx_create(device, ctypes.c_void_p(stream or None), ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().pyci_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def synchronize(self):
+        check(lib().pyci_ctx_synchronize(self.handle))
+
+    def init_comm(self, rank, nranks, unique_id):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128) if nranks > 1 else None
+        check(lib().pyci_ctx_init_comm(self.handle, rank, nranks, buf))
+
+    @property
+    def launches(self):
+        return lib().pyci_ctx_launch_count(self.handle)
+
+    def reset_launches(self):
+        lib().pyci_ctx_reset_launch_count(self.handle)
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    check(lib().pyci_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Ham:
+    """pyci_ham: integrals resident in HBM."""
+
+    def __init__(self, ctx, nbasis, ecore, one_mo=None, two_mo=None, h=None, v=None, w=None):
+        self.keep = [_f64(a) for a in (one_mo, two_mo, h, v, w)]
+        self.handle = ctypes.c_void_p()
+        check(lib().pyci_ham_upload(ctx.handle, nbasis, float(ecore), *[_ptr(a) for a in self.keep],
+                                    ctypes.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            lib().pyci_ham_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+class Wfn:
+    """pyci_wfn: determinant array + hash index resident in HBM."""
+
+    def __init__(self, ctx, kind, nbasis, nocc_up, nocc_dn, dets):
+        dets = np.ascontiguousarray(dets, dtype=np.uint64)
+        self.ndet = int(dets.shape[0])
+        self.handle = ctypes.c_void_p()
+        check(lib().pyci_wfn_upload(ctx.handle, kind, nbasis, nocc_up, nocc_dn, self.ndet, _ptr(dets),
+                                    ctypes.byref(self.handle)))
+
+    def reindex(self):
+        check(lib().pyci_wfn_reindex(self.handle))
+        return lib().pyci_wfn_index_seconds(self.handle)
+
+    def index_dets(self, dets):
+        dets = np.ascontiguousarray(dets, dtype=np.uint64)
+        out = np.empty(dets.shape[0], dtype=np.int64)
+        check(lib().pyci_wfn_index_dets(self.handle, dets.shape[0], _ptr(dets), _ptr(out)))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().pyci_wfn_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
+class Op:
+    """pyci_op: CSR row shard resident in HBM."""
+
+    def __init__(self, ctx, ham, wfn, nrow=-1, ncol=-1, symmetric=True):
+        self.handle = ctypes.c_void_p()
+        check(lib().pyci_op_build(ctx.handle, ham.handle, wfn.handle, nrow, ncol, int(bool(symmetric)),
+                                  ctypes.byref(self.handle)))
+        L = lib()
+        self.nrow, self.ncol = L.pyci_op_nrow(self.handle), L.pyci_op_ncol(self.handle)
+        self.row_begin, self.row_count = L.pyci_op_row_begin(self.handle), L.pyci_op_row_count(self.handle)
+        self.size, self.stored_nnz = L.pyci_op_size(self.handle), L.pyci_op_stored_nnz(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().pyci_op_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def build_times(self):
+        t = np.zeros(4)
+        check(lib().pyci_op_build_times(self.handle, _ptr(t)))
+        return dict(index=t[0], count_scan=t[1], fill_sort=t[2], total=t[3])
+
+    def export_csr(self):
+        indptr = np.empty(self.row_count + 1, dtype=np.int64)
+        check(lib().pyci_op_export_csr(self.handle, _ptr(indptr), None, None))
+        indices = np.empty(indptr[-1], dtype=np.int64)
+        data = np.empty(indptr[-1], dtype=np.float64)
+        check(lib().pyci_op_export_csr(self.handle, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def matvec(self, x, out=None):
+        x = _f64(x)
+        y = np.empty(self.nrow) if out is None else out
+        check(lib().pyci_op_matvec(self.handle, _ptr(x), _ptr(y)))
+        return y
+
+    def matvec_dev(self, x_dev_ptr, y_dev_ptr):
+        check(lib().pyci_op_matvec_dev(self.handle, ctypes.c_void_p(x_dev_ptr), ctypes.c_void_p(y_dev_ptr)))
+
+    def time_spmv(self, warmup=3, reps=10, flush_bytes=0):
+        ms = np.zeros(reps)
+        check(lib().pyci_op_time_spmv(self.handle, warmup, reps, flush_bytes, _ptr(ms)))
+        return ms
+
+    def get_element(self, i, j):
+        v = ctypes.c_double(0.0)
+        check(lib().pyci_op_get_element(self.handle, i, j, ctypes.byref(v)))
+        return v.value
+
+    def solve(self, n=1, c0=None, ncv=-1, maxiter=-1, tol=1e-12):
+        evals = np.empty(n)
+        evecs = np.empty((n, self.nrow))
+        stats = SolveStats()
+        c0 = _f64(c0)
+        check(lib().pyci_op_solve(self.handle, n, _ptr(c0), ncv, maxiter, tol, _ptr(evals), _ptr(evecs),
+                                  ctypes.byref(stats)))
+        return evals, evecs, {f: getattr(stats, f) for f, _ in SolveStats._fields_}
+
+
+def compute_rdms(ctx, wfn, kind, nbasis, coeffs):
+    n = nbasis
+    if kind == DOCI:
+        r1, r2 = np.empty((n, n)), np.empty((n, n))
+    elif kind == FULLCI:
+        r1, r2 = np.empty((2, n, n)), np.empty((3, n, n, n, n))
+    else:
+        r1, r2 = np.empty((n, n)), np.empty((n, n, n, n))
+    c = _f64(coeffs)
+    check(lib().pyci_compute_rdms(ctx.handle, wfn.handle, _ptr(c), _ptr(r1), _ptr(r2)))
+    return r1, r2

@@ -323,6 +323,17 @@ void pyci_wfn_destroy(pyci_wfn *wfn) {
     delete wfn;
 }
 
+int pyci_wfn_reindex(pyci_wfn *wfn) {
+    if (!wfn)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(wfn->ctx));
+    PYCI_CUDA(cudaFree(wfn->slots));
+    wfn->slots = nullptr;
+    return wfn_build_index(wfn);
+}
+
+double pyci_wfn_index_seconds(const pyci_wfn *wfn) { return wfn ? wfn->hash_seconds : 0.0; }
+
 int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) {
     if (!wfn || (n > 0 && (!dets || !out)))
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
