@@ -439,7 +439,7 @@ def run_b200(args, spec, rank, world, local):
                 "call": "pyci_b200.sparse_op(ham, wfn); op.indptr()  (host arrays in, pageable)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "spmv_warp_per_row", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "spmv_rows", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                      "frac": spmv_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": int(spmv_bytes), "ms_per_launch": spmv_ms},
         "roofline_build": {"kernel": "fill_kernel", "bound": "hbm", "achieved": fill_gbs, "peak": peak, "unit": "GB/s",

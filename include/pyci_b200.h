@@ -135,6 +135,10 @@ PYCI_API int pyci_op_matvec_dev(pyci_op *op, const double *x_dev, double *y_dev)
  * pseudo-random x, each timed with CUDA events on the context's stream; ms[reps] receives the per-launch
  * device times.  flush_bytes > 0 overwrites a scratch buffer of that size before every launch (evicts L2). */
 PYCI_API int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, double *ms);
+/* Launch shape of the SpMV kernel: threads cooperating on one row (32, 64, 128, 256, or 0 = chosen from
+ * the mean row length) and resident CTAs of 256 threads per SM (default 4).  A tuning knob only: results
+ * are identical for every shape up to the summation order inside a row. */
+PYCI_API int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_per_sm);
 /* SparseOp::get_element (sparseop.cpp:89-94); i must be a row of this rank */
 PYCI_API int pyci_op_get_element(pyci_op *op, long i, long j, double *out);
 

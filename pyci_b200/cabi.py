@@ -62,6 +62,7 @@ PROTOTYPES = {
     "pyci_op_matvec": (_i, [_vp, _vp, _vp]),
     "pyci_op_matvec_dev": (_i, [_vp, _vp, _vp]),
     "pyci_op_time_spmv": (_i, [_vp, _i, _i, _l, _vp]),
+    "pyci_op_set_spmv_shape": (_i, [_vp, _i, _i]),
     "pyci_op_get_element": (_i, [_vp, _l, _l, _vp]),
     "pyci_op_solve": (_i, [_vp, _l, _vp, _l, _l, _d, _vp, _vp, ctypes.POINTER(SolveStats)]),
     "pyci_compute_rdms": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -221,6 +222,9 @@ class Op:
         ms = np.zeros(reps)
         check(lib().pyci_op_time_spmv(self.handle, warmup, reps, flush_bytes, _ptr(ms)))
         return ms
+
+    def set_spmv_shape(self, threads_per_row=0, ctas_per_sm=4):
+        check(lib().pyci_op_set_spmv_shape(self.handle, threads_per_row, ctas_per_sm))
 
     def get_element(self, i, j):
         v = ctypes.c_double(0.0)

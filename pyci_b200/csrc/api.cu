@@ -19,8 +19,13 @@ void pyci_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static thread_local cudaStream_t g_stream = nullptr;
+
+cudaStream_t dev_current_stream() { return g_stream; }
+
 int ctx_activate(const pyci_ctx *ctx) {
     PYCI_CUDA(cudaSetDevice(ctx->device));
+    g_stream = ctx->stream;
     return PYCI_OK;
 }
 
@@ -42,7 +47,7 @@ long binom_l(long n, long k) {
 
 template<class T>
 int upload(T **dst, const T *src, size_t count, cudaStream_t st) {
-    PYCI_CUDA(cudaMalloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
+    PYCI_CUDA(dev_malloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
     if (count)
         PYCI_CUDA(cudaMemcpyAsync(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, st));
     return PYCI_OK;
@@ -156,6 +161,13 @@ int pyci_ctx_create(int device, void *stream, pyci_ctx **out) {
     PYCI_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    {
+        // keep freed blocks in the pool (see dev_malloc)
+        cudaMemPool_t pool = nullptr;
+        PYCI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ULL;
+        PYCI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (int i = 0; i < 4; ++i)
         PYCI_CUDA(cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
@@ -241,12 +253,12 @@ int pyci_ham_upload(pyci_ctx *ctx, long nbasis, double ecore, const double *one_
 void pyci_ham_destroy(pyci_ham *ham) {
     if (!ham)
         return;
-    cudaSetDevice(ham->ctx->device);
-    cudaFree(ham->one_mo);
-    cudaFree(ham->two_mo);
-    cudaFree(ham->h);
-    cudaFree(ham->v);
-    cudaFree(ham->w);
+    ctx_activate(ham->ctx);
+    dev_free(ham->one_mo);
+    dev_free(ham->two_mo);
+    dev_free(ham->h);
+    dev_free(ham->v);
+    dev_free(ham->w);
     delete ham;
 }
 
@@ -317,9 +329,9 @@ int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long noc
 void pyci_wfn_destroy(pyci_wfn *wfn) {
     if (!wfn)
         return;
-    cudaSetDevice(wfn->ctx->device);
-    cudaFree(wfn->dets);
-    cudaFree(wfn->slots);
+    ctx_activate(wfn->ctx);
+    dev_free(wfn->dets);
+    dev_free(wfn->slots);
     delete wfn;
 }
 
@@ -327,7 +339,7 @@ int pyci_wfn_reindex(pyci_wfn *wfn) {
     if (!wfn)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     PYCI_TRY(ctx_activate(wfn->ctx));
-    PYCI_CUDA(cudaFree(wfn->slots));
+    PYCI_CUDA(dev_free(wfn->slots));
     wfn->slots = nullptr;
     return wfn_build_index(wfn);
 }
@@ -344,9 +356,9 @@ int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) 
     u64 *d = nullptr;
     long *o = nullptr;
     PYCI_TRY(upload(&d, (const u64 *)dets, (size_t)n * wfn->nwords, ctx->stream));
-    cudaError_t e = cudaMalloc(&o, sizeof(long) * n);
+    cudaError_t e = dev_malloc(&o, sizeof(long) * n);
     if (e != cudaSuccess) {
-        cudaFree(d);
+        dev_free(d);
         PYCI_CUDA(e);
     }
     int rc = wfn_index_dets_impl(wfn, n, d, o);
@@ -359,8 +371,8 @@ int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) 
             rc = PYCI_ERR_CUDA;
         }
     }
-    cudaFree(d);
-    cudaFree(o);
+    dev_free(d);
+    dev_free(o);
     return rc;
 }
 
@@ -395,7 +407,7 @@ int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long 
     op->nloc = std::min(nrow, op->npad * (ctx->rank + 1)) - op->row0;
     int rc = PYCI_OK;
     auto alloc = [&](void **p, size_t bytes) {
-        if (rc == PYCI_OK && cudaMalloc(p, std::max<size_t>(bytes, 8)) != cudaSuccess) {
+        if (rc == PYCI_OK && dev_malloc(p, std::max<size_t>(bytes, 8)) != cudaSuccess) {
             pyci_set_error("device allocation of %zu bytes failed", bytes);
             cudaGetLastError();
             rc = PYCI_ERR_MEMORY;
@@ -420,14 +432,14 @@ int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long 
 void pyci_op_destroy(pyci_op *op) {
     if (!op)
         return;
-    cudaSetDevice(op->ctx->device);
-    cudaFree(op->indptr);
-    cudaFree(op->cols);
-    cudaFree(op->vals);
-    cudaFree(op->lowcnt);
-    cudaFree(op->diag);
-    cudaFree(op->xbuf);
-    cudaFree(op->ybuf);
+    ctx_activate(op->ctx);
+    dev_free(op->indptr);
+    dev_free(op->cols);
+    dev_free(op->vals);
+    dev_free(op->lowcnt);
+    dev_free(op->diag);
+    dev_free(op->xbuf);
+    dev_free(op->ybuf);
     delete op;
 }
 
@@ -459,7 +471,7 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
     }
     // output row pointer: the full row (general) or its col <= row prefix (symmetric, sparseop.cpp:223,262,431)
     long *outptr = nullptr;
-    PYCI_CUDA(cudaMalloc(&outptr, sizeof(long) * (size_t)(nloc + 1)));
+    PYCI_CUDA(dev_malloc(&outptr, sizeof(long) * (size_t)(nloc + 1)));
     if (op->symmetric) {
         prefix_from_counts<<<1, 1024, 0, st>>>(op->lowcnt, nloc, outptr);
         ctx->launches++;
@@ -487,8 +499,8 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
             if (cnt > 0) {
                 if (!didx) {
                     const long c = std::max(cnt, std::min(cap, chunk_entries));
-                    PYCI_CUDA(cudaMalloc(&didx, sizeof(long) * (size_t)c));
-                    PYCI_CUDA(cudaMalloc(&dval, sizeof(double) * (size_t)c));
+                    PYCI_CUDA(dev_malloc(&didx, sizeof(long) * (size_t)c));
+                    PYCI_CUDA(dev_malloc(&dval, sizeof(double) * (size_t)c));
                 }
                 // outptr shifted so that this chunk starts at 0 of the staging buffers
                 export_lower_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(op->indptr + r0, op->cols, op->vals, nullptr,
@@ -503,10 +515,10 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
             }
             r0 = r1;
         }
-        cudaFree(didx);
-        cudaFree(dval);
+        dev_free(didx);
+        dev_free(dval);
     }
-    cudaFree(outptr);
+    dev_free(outptr);
     return rc;
 }
 
@@ -528,9 +540,9 @@ int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
         PYCI_FAIL(PYCI_ERR_TYPE, "symmetric operator must be square for matvec");
     const long R = ctx->nranks;
     if (!op->xbuf)
-        PYCI_CUDA(cudaMalloc(&op->xbuf, sizeof(double) * (size_t)std::max<long>(op->ncol, 1)));
+        PYCI_CUDA(dev_malloc(&op->xbuf, sizeof(double) * (size_t)std::max<long>(op->ncol, 1)));
     if (!op->ybuf) {
-        PYCI_CUDA(cudaMalloc(&op->ybuf, sizeof(double) * (size_t)(op->npad * (R + 1))));
+        PYCI_CUDA(dev_malloc(&op->ybuf, sizeof(double) * (size_t)(op->npad * (R + 1))));
         PYCI_CUDA(cudaMemsetAsync(op->ybuf, 0, sizeof(double) * (size_t)(op->npad * (R + 1)), ctx->stream));
     }
     PYCI_CUDA(cudaMemcpyAsync(op->xbuf, x, sizeof(double) * op->ncol, cudaMemcpyHostToDevice, ctx->stream));
@@ -546,6 +558,19 @@ int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
     return PYCI_OK;
 }
 
+int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_per_sm) {
+    if (!op)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (threads_per_row != 0 && threads_per_row != 32 && threads_per_row != 64 && threads_per_row != 128 &&
+        threads_per_row != 256)
+        PYCI_FAIL(PYCI_ERR_VALUE, "threads_per_row must be 0 (automatic), 32, 64, 128 or 256");
+    if (ctas_per_sm < 1 || ctas_per_sm > 32)
+        PYCI_FAIL(PYCI_ERR_VALUE, "ctas_per_sm must be in [1, 32]");
+    op->spmv_tpr = threads_per_row;
+    op->spmv_ctas = ctas_per_sm;
+    return PYCI_OK;
+}
+
 int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, double *ms) {
     if (!op || !ms || reps < 1)
         PYCI_FAIL(PYCI_ERR_VALUE, "bad argument");
@@ -555,10 +580,10 @@ int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, doubl
     double *x = nullptr, *y = nullptr;
     void *flush = nullptr;
     const long nx = std::max<long>(op->ncol, 1);
-    PYCI_CUDA(cudaMalloc(&x, sizeof(double) * nx));
-    PYCI_CUDA(cudaMalloc(&y, sizeof(double) * std::max<long>(op->nloc, 1)));
+    PYCI_CUDA(dev_malloc(&x, sizeof(double) * nx));
+    PYCI_CUDA(dev_malloc(&y, sizeof(double) * std::max<long>(op->nloc, 1)));
     if (flush_bytes > 0)
-        PYCI_CUDA(cudaMalloc(&flush, (size_t)flush_bytes));
+        PYCI_CUDA(dev_malloc(&flush, (size_t)flush_bytes));
     std::vector<double> hx((size_t)nx);
     u64 sdd = 0x9e3779b97f4a7c15ULL;
     for (long i = 0; i < nx; ++i) {
@@ -590,9 +615,9 @@ int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, doubl
     }
     for (auto &e : ev)
         cudaEventDestroy(e);
-    cudaFree(x);
-    cudaFree(y);
-    cudaFree(flush);
+    dev_free(x);
+    dev_free(y);
+    dev_free(flush);
     return rc;
 }
 
@@ -641,16 +666,20 @@ int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long maxiter,
         PYCI_FAIL(PYCI_ERR_TYPE, "Can only solve sparse symmetric matrix operators");
     if (nrow == 1) {
         double h00 = 0.0;
-        if (ctx->rank == 0)
-            PYCI_CUDA(cudaMemcpy(&h00, op->diag, sizeof(double), cudaMemcpyDeviceToHost));
+        cudaStream_t st = ctx->stream;
+        if (ctx->rank == 0) {
+            PYCI_CUDA(cudaMemcpyAsync(&h00, op->diag, sizeof(double), cudaMemcpyDeviceToHost, st));
+            PYCI_CUDA(cudaStreamSynchronize(st));
+        }
         if (ctx->nranks > 1) {
             // every rank must return the same value; rank 0 holds row 0
             double *d = nullptr;
-            PYCI_CUDA(cudaMalloc(&d, sizeof(double)));
-            PYCI_CUDA(cudaMemcpy(d, &h00, sizeof(double), cudaMemcpyHostToDevice));
+            PYCI_CUDA(dev_malloc(&d, sizeof(double)));
+            PYCI_CUDA(cudaMemcpyAsync(d, &h00, sizeof(double), cudaMemcpyHostToDevice, st));
             PYCI_TRY(comm_allreduce_sum_f64(ctx, d, 1));
-            PYCI_CUDA(cudaMemcpy(&h00, d, sizeof(double), cudaMemcpyDeviceToHost));
-            cudaFree(d);
+            PYCI_CUDA(cudaMemcpyAsync(&h00, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+            PYCI_CUDA(cudaStreamSynchronize(st));
+            dev_free(d);
         }
         evals[0] = h00 + op->ecore;
         evecs[0] = 1.0;

@@ -21,116 +21,227 @@ namespace {
 // ---- matrix elements, in the reference's operation order ------------------------------------
 
 // DOCI diagonal, sparseop.cpp:228-236,253: val1 + 2*val2
-__device__ double diag_doci(const BuildParams &P, const RowShared &rs) {
-    const int n = P.n, no = rs.nocc[0];
+__device__ double diag_doci(const BuildParams &P, u64 det) {
+    const int n = P.n;
     double val1 = 0.0, val2 = 0.0;
-    for (int i = 0; i < no; ++i) {
-        const int k = rs.occ[0][i];
+    for (u64 wi = det; wi; wi &= wi - 1) {
+        const int k = __ffsll((long long)wi) - 1;
         val1 += __ldg(P.v + k * (n + 1));
         val2 += __ldg(P.h + k);
-        for (int j = i + 1; j < no; ++j)
-            val2 += __ldg(P.w + k * n + rs.occ[0][j]);
+        for (u64 wj = wi & (wi - 1); wj; wj &= wj - 1)
+            val2 += __ldg(P.w + k * n + (__ffsll((long long)wj) - 1));
     }
     return val1 + val2 * 2;
 }
 
-// FullCI diagonal, sparseop.cpp:283-292,367-372 (GenCI :443-449 is the alpha-only part)
-template<int KIND>
-__device__ double diag_twobody(const BuildParams &P, const RowShared &rs) {
+// FullCI diagonal, sparseop.cpp:283-292,367-372 (GenCI :443-449 is the alpha-only part); occupied
+// orbitals are visited in ascending order like fill_occs does
+__device__ double diag_twobody(const BuildParams &P, u64 da, u64 db) {
     const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
-    const int na = rs.nocc[0], nb = (KIND == PYCI_FULLCI) ? rs.nocc[1] : 0;
     double val2 = 0.0;
-    for (int i = 0; i < na; ++i) {
-        const long ii = rs.occ[0][i], ioff = n3 * ii;
+    for (u64 wi = da; wi; wi &= wi - 1) {
+        const long ii = __ffsll((long long)wi) - 1, ioff = n3 * ii;
         val2 += __ldg(P.one_mo + (n1 + 1) * ii);
-        for (int k = i + 1; k < na; ++k) {
-            const long kk = rs.occ[0][k], koff = ioff + n2 * kk;
+        for (u64 wk = wi & (wi - 1); wk; wk &= wk - 1) {
+            const long kk = __ffsll((long long)wk) - 1, koff = ioff + n2 * kk;
             val2 += __ldg(P.two_mo + koff + n1 * ii + kk) - __ldg(P.two_mo + koff + n1 * kk + ii);
         }
-        for (int k = 0; k < nb; ++k) {
-            const long kk = rs.occ[1][k];
+        for (u64 wk = db; wk; wk &= wk - 1) {
+            const long kk = __ffsll((long long)wk) - 1;
             val2 += __ldg(P.two_mo + ioff + n2 * kk + n1 * ii + kk);
         }
     }
-    for (int i = 0; i < nb; ++i) {
-        const long ii = rs.occ[1][i], ioff = n3 * ii;
+    for (u64 wi = db; wi; wi &= wi - 1) {
+        const long ii = __ffsll((long long)wi) - 1, ioff = n3 * ii;
         val2 += __ldg(P.one_mo + (n1 + 1) * ii);
-        for (int k = i + 1; k < nb; ++k) {
-            const long kk = rs.occ[1][k], koff = ioff + n2 * kk;
+        for (u64 wk = wi & (wi - 1); wk; wk &= wk - 1) {
+            const long kk = __ffsll((long long)wk) - 1, koff = ioff + n2 * kk;
             val2 += __ldg(P.two_mo + koff + n1 * ii + kk) - __ldg(P.two_mo + koff + n1 * kk + ii);
         }
     }
     return val2;
 }
 
+// one thread per row: H_ii of this rank's rows (also the Davidson preconditioner)
 template<int KIND>
-__device__ double element(const BuildParams &P, const RowShared &rs, u32 code) {
-    const int type = code >> 24;
-    const long i = (code >> 18) & 63, a = (code >> 12) & 63, k = (code >> 6) & 63, l = code & 63;
+__global__ void diag_kernel(BuildParams P) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.nloc)
+        return;
+    const long row = P.row0 + r;
+    const u64 a = P.dets[row * P.nwords], b = (KIND == PYCI_FULLCI) ? P.dets[row * P.nwords + 1] : 0ULL;
+    P.diag[r] = (KIND == PYCI_DOCI) ? diag_doci(P, a) : diag_twobody(P, a, b);
+}
+
+// ---- per-row excitation tables ---------------------------------------------------------------------
+// Single excitations of the row determinant, built once per row in shared memory (structure of arrays):
+// excited string, signed matrix element (fill pass only), partial two_mo offset and packed (i, a, parity).
+// Alpha-beta doubles are then one table entry per spin; same-spin doubles use the static pair table.
+struct RowTables {
+    u64 *sa_str, *sb_str;
+    double *sa_val, *sb_val;
+    u32 *sa_off, *sb_off, *sa_meta, *sb_meta;
+};
+
+__host__ __device__ inline size_t tables_bytes(u32 nSa, u32 nSb) { return (size_t)24 * ((nSa + 1) & ~1u) + (size_t)24 * ((nSb + 1) & ~1u); }
+
+__device__ __forceinline__ RowTables carve_tables(unsigned char *base, u32 nSa, u32 nSb) {
+    const u32 ea = (nSa + 1) & ~1u, eb = (nSb + 1) & ~1u;
+    RowTables T;
+    T.sa_str = reinterpret_cast<u64 *>(base);
+    T.sb_str = T.sa_str + ea;
+    T.sa_val = reinterpret_cast<double *>(T.sb_str + eb);
+    T.sb_val = T.sa_val + ea;
+    T.sa_off = reinterpret_cast<u32 *>(T.sb_val + eb);
+    T.sb_off = T.sa_off + ea;
+    T.sa_meta = T.sb_off + eb;
+    T.sb_meta = T.sa_meta + ea;
+    return T;
+}
+
+template<int KIND, bool VAL>
+__device__ __forceinline__ void build_tables(const BuildParams &P, const RowShared &rs, const RowTables &T, u32 nSa,
+                                             u32 nSb) {
     const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
-    switch (type) {
-    case T_PAIR: // sparseop.cpp:246: v[k*n + l], no phase
-        return __ldg(P.v + i * n1 + a);
-    case T_AB: { // sparseop.cpp:330-332
-        const int par = parity_single(rs.det[0], (int)i, (int)a) ^ parity_single(rs.det[1], (int)k, (int)l);
-        return apply_sign(__ldg(P.two_mo + n3 * i + n2 * k + n1 * a + l), par);
-    }
-    case T_AA:
-    case T_BB: { // sparseop.cpp:350-353 / :408-411
-        const u64 d = rs.det[type == T_AA ? 0 : 1];
-        const long koff = n3 * i + n2 * k;
-        const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
-        return apply_sign(x, parity_double(d, (int)i, (int)k, (int)a, (int)l));
-    }
-    case T_SA: { // sparseop.cpp:303-315 (GenCI :459-466)
-        const long ioff = n3 * i;
-        double val1 = __ldg(P.one_mo + n1 * i + a);
-        const int na = rs.nocc[0], nb = (KIND == PYCI_FULLCI) ? rs.nocc[1] : 0;
-        for (int q = 0; q < na; ++q) {
-            const long kk = rs.occ[0][q], koff = ioff + n2 * kk;
-            val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
+    const int na = rs.nocc[0], nb = (KIND == PYCI_FULLCI) ? rs.nocc[1] : 0;
+    const u32 nva = (u32)P.nvir_a, nvb = (u32)P.nvir_b;
+    for (u32 t = threadIdx.x; t < nSa + nSb; t += blockDim.x) {
+        if (t < nSa) {
+            const u32 io = t / nva, ia = t - io * nva;
+            const long i = rs.occ[0][io], a = rs.vir[0][ia];
+            const int par = parity_single(rs.det[0], (int)i, (int)a);
+            T.sa_str[t] = rs.det[0] ^ (1ULL << i) ^ (1ULL << a);
+            T.sa_off[t] = (u32)(n3 * i + n1 * a);
+            T.sa_meta[t] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            if (VAL) { // sparseop.cpp:303-315 (GenCI :459-466)
+                const long ioff = n3 * i;
+                double val1 = __ldg(P.one_mo + n1 * i + a);
+                for (int q = 0; q < na; ++q) {
+                    const long kk = rs.occ[0][q], koff = ioff + n2 * kk;
+                    val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
+                }
+                for (int q = 0; q < nb; ++q) {
+                    const long kk = rs.occ[1][q];
+                    val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
+                }
+                T.sa_val[t] = apply_sign(val1, par);
+            }
+        } else {
+            const u32 tb = t - nSa;
+            const u32 io = tb / nvb, ia = tb - io * nvb;
+            const long i = rs.occ[1][io], a = rs.vir[1][ia];
+            const int par = parity_single(rs.det[1], (int)i, (int)a);
+            T.sb_str[tb] = rs.det[1] ^ (1ULL << i) ^ (1ULL << a);
+            T.sb_off[tb] = (u32)(n2 * i + a);
+            T.sb_meta[tb] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            if (VAL) { // sparseop.cpp:382-394
+                const long ioff = n3 * i;
+                double val1 = __ldg(P.one_mo + n1 * i + a);
+                for (int q = 0; q < na; ++q) {
+                    const long kk = rs.occ[0][q];
+                    val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
+                }
+                for (int q = 0; q < nb; ++q) {
+                    const long kk = rs.occ[1][q], koff = ioff + n2 * kk;
+                    val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
+                }
+                T.sb_val[tb] = apply_sign(val1, par);
+            }
         }
-        for (int q = 0; q < nb; ++q) {
-            const long kk = rs.occ[1][q];
-            val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
-        }
-        return apply_sign(val1, parity_single(rs.det[0], (int)i, (int)a));
     }
-    case T_SB: { // sparseop.cpp:382-394
-        const long ioff = n3 * i;
-        double val1 = __ldg(P.one_mo + n1 * i + a);
-        const int na = rs.nocc[0], nb = rs.nocc[1];
-        for (int q = 0; q < na; ++q) {
-            const long kk = rs.occ[0][q];
-            val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
-        }
-        for (int q = 0; q < nb; ++q) {
-            const long kk = rs.occ[1][q], koff = ioff + n2 * kk;
-            val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
-        }
-        return apply_sign(val1, parity_single(rs.det[1], (int)i, (int)a));
+}
+
+// candidate c of the row -> excited strings (A, B) and, in the fill pass, the signed matrix element.
+// Segment order: alpha-beta doubles | alpha-alpha doubles | beta-beta doubles | alpha singles | beta singles;
+// consecutive candidates (the lanes of a warp) share a segment, so evaluation does not diverge.
+template<int KIND, bool VAL>
+__device__ __forceinline__ void candidate(const BuildParams &P, const RowShared &rs, const RowTables &T,
+                                          const uchar2 *__restrict__ pairs, u32 c, u64 &A, u64 &B, double &val) {
+    const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
+    A = rs.det[0];
+    B = rs.det[1];
+    if (KIND == PYCI_DOCI) { // pair excitation k -> l, element v[k,l], no phase (sparseop.cpp:237-249)
+        const u32 io = fdiv(c, P.dVa), ia = c - io * (u32)P.nvir_a;
+        const int k = rs.occ[0][io], l = rs.vir[0][ia];
+        A ^= (1ULL << k) | (1ULL << l);
+        if (VAL)
+            val = __ldg(P.v + k * n1 + l);
+        return;
     }
-    default: // T_DIAG
-        return (KIND == PYCI_DOCI) ? diag_doci(P, rs) : diag_twobody<KIND>(P, rs);
+    if (KIND == PYCI_FULLCI) {
+        if (c < P.nAB) { // sparseop.cpp:318-337
+            const u32 sa = fdiv(c, P.dSb), sb = c - sa * P.nSb;
+            A = T.sa_str[sa];
+            B = T.sb_str[sb];
+            if (VAL) {
+                const int par = ((T.sa_meta[sa] ^ T.sb_meta[sb]) >> 16) & 1;
+                val = apply_sign(__ldg(P.two_mo + (T.sa_off[sa] + T.sb_off[sb])), par);
+            }
+            return;
+        }
+        c -= P.nAB;
     }
+    if (c < P.nDa) { // sparseop.cpp:339-358 (GenCI :470-490)
+        const u32 po = fdiv(c, P.dPva), pv = c - po * P.nPva;
+        const uchar2 o = pairs[po], v = pairs[pv];
+        const long i = rs.occ[0][o.x], k = rs.occ[0][o.y], a = rs.vir[0][v.x], l = rs.vir[0][v.y];
+        A ^= (1ULL << i) | (1ULL << k) | (1ULL << a) | (1ULL << l);
+        if (VAL) {
+            const long koff = n3 * i + n2 * k;
+            const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
+            val = apply_sign(x, parity_double(rs.det[0], (int)i, (int)k, (int)a, (int)l));
+        }
+        return;
+    }
+    c -= P.nDa;
+    if (KIND == PYCI_FULLCI) {
+        if (c < P.nDb) { // sparseop.cpp:397-416
+            const u32 po = fdiv(c, P.dPvb), pv = c - po * P.nPvb;
+            const uchar2 o = pairs[po], v = pairs[pv];
+            const long i = rs.occ[1][o.x], k = rs.occ[1][o.y], a = rs.vir[1][v.x], l = rs.vir[1][v.y];
+            B ^= (1ULL << i) | (1ULL << k) | (1ULL << a) | (1ULL << l);
+            if (VAL) {
+                const long koff = n3 * i + n2 * k;
+                const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
+                val = apply_sign(x, parity_double(rs.det[1], (int)i, (int)k, (int)a, (int)l));
+            }
+            return;
+        }
+        c -= P.nDb;
+    }
+    if (c < P.nSa) {
+        A = T.sa_str[c];
+        if (VAL)
+            val = T.sa_val[c];
+        return;
+    }
+    c -= P.nSa;
+    B = T.sb_str[c];
+    if (VAL)
+        val = T.sb_val[c];
 }
 
 constexpr int UNROLL = 4;
 
 // ---- count pass ---------------------------------------------------------------------------------
 template<int KIND, int KM>
-__global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> index, int npairs_dim) {
+__global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw);
+    const RowTables T = carve_tables(smem_raw, nSa, nSb);
+    uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw + tables_bytes(nSa, nSb));
     __shared__ RowShared rs;
     __shared__ int warp_sums[8];
-    fill_pairs(pairs, npairs_dim);
+    fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
     for (long r = blockIdx.x; r < P.nloc; r += gridDim.x) {
         const long row = P.row0 + r;
         __syncthreads();
         row_setup(rs, P, row, nspin);
         __syncthreads();
+        if (KIND != PYCI_DOCI) {
+            build_tables<KIND, false>(P, rs, T, nSa, nSb);
+            __syncthreads();
+        }
         int cnt = 0;
         for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
             int hit[UNROLL];
@@ -140,8 +251,8 @@ __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> 
                 hit[u] = -1;
                 if (c < P.ncand) {
                     u64 A, B;
-                    u32 code;
-                    decode<KIND>(P, rs, pairs, c, A, B, code);
+                    double unused;
+                    candidate<KIND, false>(P, rs, T, pairs, c, A, B, unused);
                     hit[u] = index.find(A, B);
                 }
             }
@@ -166,50 +277,139 @@ __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> 
 
 // ---- fill pass ----------------------------------------------------------------------------------
 
-// sort buf[0,m) ascending; normalised bitonic network (all comparators ascending), virtual +inf padding
-__device__ void block_sort(u64 *buf, int m) {
-    int P2 = 1;
-    while (P2 < m)
-        P2 <<= 1;
-    const int half = P2 >> 1;
-    for (int k = 2; k <= P2; k <<= 1) {
-        // flip step
-        for (int t = threadIdx.x; t < half; t += blockDim.x) {
-            const int hk = k >> 1;
-            const int blk = t / hk, off = t - blk * hk;
-            const int i = blk * k + off, j = blk * k + (k - 1 - off);
-            if (j < m) {
-                const u64 x = buf[i], y = buf[j];
-                if (x > y) {
-                    buf[i] = y;
-                    buf[j] = x;
-                }
+// lanes of the warp holding the same digit as this lane (valid lanes only): dbits ballots, independent
+// of how many distinct digits the warp holds (match.any serialises over the distinct values)
+__device__ __forceinline__ u32 digit_peers(u32 d, bool valid, int dbits) {
+    u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+        if (bit < dbits) {
+            const bool on = (d >> bit) & 1u;
+            const u32 bal = __ballot_sync(0xffffffffu, on);
+            peers &= on ? bal : ~bal;
+        }
+    }
+    return peers;
+}
+
+// Stable LSD radix sort of a[0,m) (ping-pong with b) on key bits [32, 32 + passes*dbits): the per-row
+// sort_row of sparseop.cpp:214-218.  Each warp owns a contiguous slice of the row and a private counter
+// row hist[w][bin]; lanes holding equal digits are grouped by ballots so that a counter is touched by one
+// lane, which keeps the scatter stable without atomics.  Returns the buffer holding the result.
+__device__ u64 *block_radix_sort(u64 *a, u64 *b, int m, int passes, int dbits, u32 *hist, u32 *tot) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    const int nbins = 1 << dbits;
+    const u32 dmask = (u32)(nbins - 1);
+    const int seg = (((m + nw - 1) / nw) + 31) & ~31;
+    const int begin = min(m, w * seg), end = min(m, begin + seg);
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = 32 + pass * dbits;
+        for (int t = threadIdx.x; t < nw * nbins; t += blockDim.x)
+            hist[t] = 0;
+        __syncthreads();
+        u32 *myhist = hist + w * nbins;
+        // count: order does not matter, leaders add with shared-memory atomics, two chunks in flight
+        for (int base = begin; base < end; base += 64) {
+            const int i0 = base + lane, i1 = base + 32 + lane;
+            const bool v0 = i0 < end, v1 = i1 < end;
+            const u32 d0 = v0 ? (u32)(a[i0] >> shift) & dmask : 0u;
+            const u32 d1 = v1 ? (u32)(a[i1] >> shift) & dmask : 0u;
+            const u32 p0 = digit_peers(d0, v0, dbits);
+            const u32 p1 = digit_peers(d1, v1, dbits);
+            if (v0 && lane == __ffs(p0) - 1)
+                atomicAdd(&myhist[d0], (u32)__popc(p0));
+            if (v1 && lane == __ffs(p1) - 1)
+                atomicAdd(&myhist[d1], (u32)__popc(p1));
+        }
+        __syncthreads();
+        // exclusive scan in (bin, warp) order
+        for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
+            u32 run = 0;
+            for (int q = 0; q < nw; ++q) {
+                const u32 t = hist[q * nbins + bin];
+                hist[q * nbins + bin] = run;
+                run += t;
+            }
+            tot[bin] = run;
+        }
+        __syncthreads();
+        if (w == 0) {
+            const int per = nbins >> 5; // nbins >= 32
+            u32 local = 0;
+            for (int q = 0; q < per; ++q)
+                local += tot[lane * per + q];
+            u32 incl = local;
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            u32 run = incl - local;
+            for (int q = 0; q < per; ++q) {
+                const u32 t = tot[lane * per + q];
+                tot[lane * per + q] = run;
+                run += t;
             }
         }
         __syncthreads();
-        for (int js = k >> 2; js >= 1; js >>= 1) {
-            for (int t = threadIdx.x; t < half; t += blockDim.x) {
-                const int i = 2 * js * (t / js) + (t % js), j = i + js;
-                if (j < m) {
-                    const u64 x = buf[i], y = buf[j];
-                    if (x > y) {
-                        buf[i] = y;
-                        buf[j] = x;
-                    }
+        for (int t = threadIdx.x; t < nw * nbins; t += blockDim.x)
+            hist[t] += tot[t & (nbins - 1)];
+        __syncthreads();
+        // scatter in slice order; the keys / ballots of the next chunk are prepared before the counter
+        // read-modify-write of the current one
+        {
+            int idx = begin + lane;
+            bool valid = idx < end;
+            u64 k = valid ? a[idx] : 0ULL;
+            u32 d = (u32)(k >> shift) & dmask;
+            u32 peers = digit_peers(d, valid, dbits);
+            for (int base = begin; base < end; base += 32) {
+                const int nidx = base + 32 + lane;
+                const bool nvalid = nidx < end;
+                const u64 nk = nvalid ? a[nidx] : 0ULL;
+                const u32 nd = (u32)(nk >> shift) & dmask;
+                const u32 npeers = (base + 32 < end) ? digit_peers(nd, nvalid, dbits) : 0u;
+                u32 pos = 0;
+                if (valid)
+                    pos = myhist[d] + __popc(peers & lt);
+                __syncwarp();
+                if (valid) {
+                    b[pos] = k;
+                    if (lane == __ffs(peers) - 1)
+                        myhist[d] += __popc(peers);
                 }
+                __syncwarp();
+                valid = nvalid;
+                k = nk;
+                d = nd;
+                peers = npeers;
             }
-            __syncthreads();
         }
+        __syncthreads();
+        u64 *t = a;
+        a = b;
+        b = t;
     }
+    return a;
 }
 
 template<int KIND, int KM>
-__global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, int npairs_dim) {
+__global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *buf = reinterpret_cast<u64 *>(smem_raw);
-    uchar2 *pairs = reinterpret_cast<uchar2 *>(buf + P.maxrow);
+    // layout: keys A | keys B | values | radix counters | excitation tables | pair table
+    u64 *keyA = reinterpret_cast<u64 *>(smem_raw);
+    u64 *keyB = keyA + P.maxrow;
+    double *valbuf = reinterpret_cast<double *>(keyB + P.maxrow);
+    u32 *hist = reinterpret_cast<u32 *>(valbuf + P.maxrow);
+    const int nbins = 1 << P.sort_dbits, nw = blockDim.x >> 5;
+    u32 *tot = hist + nw * nbins;
+    unsigned char *tbase = reinterpret_cast<unsigned char *>(tot + nbins);
+    const RowTables T = carve_tables(tbase, nSa, nSb);
+    uchar2 *pairs = reinterpret_cast<uchar2 *>(tbase + tables_bytes(nSa, nSb));
     __shared__ RowShared rs;
-    fill_pairs(pairs, npairs_dim);
+    __shared__ int low_count;
+    fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -217,20 +417,30 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         const long row = P.row0 + r;
         __syncthreads();
         row_setup(rs, P, row, nspin);
+        if (threadIdx.x == 0)
+            low_count = 0;
         __syncthreads();
-        if (threadIdx.x == 0 && row < P.ncol)
-            buf[atomicAdd(&rs.count, 1)] = ((u64)row << 32) | pack_code(T_DIAG, 0, 0, 0, 0);
+        if (KIND != PYCI_DOCI)
+            build_tables<KIND, true>(P, rs, T, nSa, nSb);
+        if (threadIdx.x == 0 && row < P.ncol) { // diagonal, sparseop.cpp:252-255 / :421-424 / :496-499
+            const int slot = atomicAdd(&rs.count, 1);
+            keyA[slot] = ((u64)row << 32) | (u32)slot;
+            valbuf[slot] = P.diag[r];
+            atomicAdd(&low_count, 1);
+        }
+        __syncthreads();
+        int nlow = 0;
         for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
             int hit[UNROLL];
-            u32 codes[UNROLL];
+            double val[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const u32 c = base + u * blockDim.x + threadIdx.x;
                 hit[u] = -1;
-                codes[u] = 0;
+                val[u] = 0.0;
                 if (c < P.ncand) {
                     u64 A, B;
-                    decode<KIND>(P, rs, pairs, c, A, B, codes[u]);
+                    candidate<KIND, true>(P, rs, T, pairs, c, A, B, val[u]);
                     hit[u] = index.find(A, B);
                 }
             }
@@ -238,38 +448,37 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
             for (int u = 0; u < UNROLL; ++u) {
                 // warp-aggregated append: one shared atomic per warp per step
                 const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
-                const u32 m = __ballot_sync(0xffffffffu, keep);
-                if (m) {
+                const u32 msk = __ballot_sync(0xffffffffu, keep);
+                if (msk) {
                     int slot = 0;
-                    const int leader = __ffs(m) - 1;
+                    const int leader = __ffs(msk) - 1;
                     if (lane == leader)
-                        slot = atomicAdd(&rs.count, __popc(m));
-                    slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(m & lt);
-                    if (keep)
-                        buf[slot] = ((u64)(u32)hit[u] << 32) | codes[u];
+                        slot = atomicAdd(&rs.count, __popc(msk));
+                    slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(msk & lt);
+                    if (keep) {
+                        keyA[slot] = ((u64)(u32)hit[u] << 32) | (u32)slot;
+                        valbuf[slot] = val[u];
+                        nlow += ((long)hit[u] <= row);
+                    }
                 }
             }
         }
+        for (int o = 16; o > 0; o >>= 1)
+            nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+        if (lane == 0 && nlow)
+            atomicAdd(&low_count, nlow);
         __syncthreads();
         const int m = rs.count;
-        block_sort(buf, m);
-        // evaluate and stream out
+        const u64 *sorted = block_radix_sort(keyA, keyB, m, P.sort_passes, P.sort_dbits, hist, tot);
+        // stream the row out: columns ascending, values gathered through the slot index
         const long out0 = P.indptr[r];
         for (int e = threadIdx.x; e < m; e += blockDim.x) {
-            const u64 kv = buf[e];
-            const long col = (long)(kv >> 32);
-            const u32 code = (u32)kv;
-            const double val = element<KIND>(P, rs, code);
-            P.cols[out0 + e] = (int)col;
-            P.vals[out0 + e] = val;
-            if ((code >> 24) == T_DIAG)
-                P.diag[r] = val;
-            // number of entries with col <= row: rows are sorted, so it is a prefix length
-            const bool le = col <= row;
-            const bool next_gt = (e + 1 == m) || ((long)(buf[e + 1] >> 32) > row);
-            if (le && next_gt)
-                P.lowcnt[r] = e + 1;
+            const u64 kv = sorted[e];
+            P.cols[out0 + e] = (int)(kv >> 32);
+            P.vals[out0 + e] = valbuf[(u32)kv];
         }
+        if (threadIdx.x == 0)
+            P.lowcnt[r] = low_count; // entries with col <= row: a prefix of the sorted row
     }
 }
 
@@ -448,14 +657,14 @@ int build_index_t(pyci_wfn *wfn) {
                                                              wfn->dets, wfn->nwords, ndet);
         ctx->launches++;
         int *bad = nullptr;
-        PYCI_CUDA(cudaMalloc(&bad, sizeof(int)));
+        PYCI_CUDA(dev_malloc(&bad, sizeof(int)));
         PYCI_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
         verify_kernel<KM><<<blocks, threads, 0, ctx->stream>>>(make_index<KM>(wfn), wfn->dets, wfn->nwords, ndet, bad);
         ctx->launches++;
         int hbad = 0;
         PYCI_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(bad);
+        dev_free(bad);
         if (hbad)
             PYCI_FAIL(PYCI_ERR_VALUE, "wave function contains %d duplicate determinant(s)", hbad);
     }
@@ -477,13 +686,16 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     const DetIndex<KM> ix = make_index<KM>(wfn);
     const long nloc = op->nloc;
     const size_t pair_bytes = pair_table_bytes(P);
+    // single-excitation tables live in shared memory (two-body kinds only)
+    const u32 nSa = (KIND == PYCI_DOCI) ? 0u : P.nSa, nSb = (KIND == PYCI_FULLCI && P.nAB > 0) ? P.nSb : 0u;
+    const size_t tab_bytes = tables_bytes(nSa, nSb);
 
     // block size from the amount of per-row work
-    auto pick_block = [](long work) { return work <= 256 ? 32 : work <= 1024 ? 64 : work <= 4096 ? 128 : 256; };
+    auto pick_block = [](long work) { return work <= 128 ? 32 : work <= 512 ? 64 : work <= 1024 ? 128 : 256; };
 
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], st));
     int *rowcnt = nullptr;
-    PYCI_CUDA(cudaMalloc(&rowcnt, sizeof(int) * (size_t)(nloc + 1)));
+    PYCI_CUDA(dev_malloc(&rowcnt, sizeof(int) * (size_t)(nloc + 1)));
     P.rowcnt = rowcnt;
     const bool analytic = wfn->complete && op->ncol == wfn->ndet;
     if (nloc > 0) {
@@ -494,9 +706,13 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
         } else {
             const int block = pick_block((long)P.ncand / 4);
             int per_sm = 1;
-            PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<KIND, KM>, block, pair_bytes));
+            const size_t csmem = tab_bytes + pair_bytes;
+            if ((long)csmem > (long)ctx->smem_optin)
+                PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "excitation tables (%zu bytes) do not fit shared memory", csmem);
+            PYCI_CUDA(cudaFuncSetAttribute(count_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<KIND, KM>, block, csmem));
             const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-            count_kernel<KIND, KM><<<(unsigned)grid, block, pair_bytes, st>>>(P, ix, npairs_dim);
+            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb);
             ctx->launches++;
         }
     }
@@ -504,8 +720,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     const long nb = (nloc + SCAN_BLOCK - 1) / SCAN_BLOCK;
     long *blocksum = nullptr;
     int *maxcnt = nullptr;
-    PYCI_CUDA(cudaMalloc(&blocksum, sizeof(long) * (size_t)(nb + 2)));
-    PYCI_CUDA(cudaMalloc(&maxcnt, sizeof(int)));
+    PYCI_CUDA(dev_malloc(&blocksum, sizeof(long) * (size_t)(nb + 2)));
+    PYCI_CUDA(dev_malloc(&maxcnt, sizeof(int)));
     PYCI_CUDA(cudaMemsetAsync(maxcnt, 0, sizeof(int), st));
     PYCI_CUDA(cudaMemsetAsync(op->indptr, 0, sizeof(long) * (size_t)(nloc + 1), st));
     if (nloc > 0) {
@@ -520,37 +736,55 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     PYCI_CUDA(cudaMemcpyAsync(&maxrow, maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st));
     PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
     PYCI_CUDA(cudaStreamSynchronize(st));
-    cudaFree(blocksum);
-    cudaFree(maxcnt);
-    cudaFree(rowcnt);
+    dev_free(blocksum);
+    dev_free(maxcnt);
+    dev_free(rowcnt);
     P.rowcnt = nullptr;
 
     op->nnz = nnz;
-    PYCI_CUDA(cudaMalloc(&op->cols, sizeof(int) * (size_t)std::max<long>(nnz, 1)));
-    PYCI_CUDA(cudaMalloc(&op->vals, sizeof(double) * (size_t)std::max<long>(nnz, 1)));
+    PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)std::max<long>(nnz, 1)));
+    PYCI_CUDA(dev_malloc(&op->vals, sizeof(double) * (size_t)std::max<long>(nnz, 1)));
     P.cols = op->cols;
     P.vals = op->vals;
     P.maxrow = (maxrow + 1) & ~1;
-    const size_t smem = sizeof(u64) * (size_t)P.maxrow + pair_bytes;
-    if ((long)smem > (long)ctx->smem_optin)
-        PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
-                  "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
-                  maxrow, (long)((ctx->smem_optin - pair_bytes) / sizeof(u64)));
+    // per-row LSD radix sort: digits of 5..8 bits covering the column index
+    {
+        int bits = 1;
+        while ((1L << bits) < std::max<long>(op->ncol, 2))
+            ++bits;
+        P.sort_passes = (bits + 7) / 8;
+        P.sort_dbits = std::max(5, (bits + P.sort_passes - 1) / P.sort_passes);
+    }
+    PYCI_CUDA(cudaEventRecord(ctx->ev[2], st)); // after the allocations: ev[2]..ev[3] brackets kernels only
     if (nloc > 0 && nnz > 0) {
-        const int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
+        diag_kernel<KIND><<<(unsigned)((nloc + 127) / 128), 128, 0, st>>>(P);
+        ctx->launches++;
+        int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
+        size_t smem = 0;
+        for (;;) { // keys (ping-pong) + values + radix counters + tables + pair table
+            smem = (size_t)24 * P.maxrow + sizeof(u32) * ((size_t)(block / 32) + 1) * (1u << P.sort_dbits) + tab_bytes +
+                   pair_bytes;
+            if ((long)smem <= (long)ctx->smem_optin || block == 32)
+                break;
+            block >>= 1;
+        }
+        if ((long)smem > (long)ctx->smem_optin)
+            PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
+                      "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
+                      maxrow, (long)((ctx->smem_optin - tab_bytes - pair_bytes - 2048) / 24));
         PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 1;
         PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM>, block, smem));
         const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-        fill_kernel<KIND, KM><<<(unsigned)grid, block, smem, st>>>(P, ix, npairs_dim);
+        fill_kernel<KIND, KM><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
         ctx->launches++;
     }
-    PYCI_CUDA(cudaEventRecord(ctx->ev[2], st));
+    PYCI_CUDA(cudaEventRecord(ctx->ev[3], st));
     PYCI_CUDA(cudaStreamSynchronize(st));
     PYCI_CUDA(cudaGetLastError());
     float ms01 = 0, ms12 = 0;
     cudaEventElapsedTime(&ms01, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ms12, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ms12, ctx->ev[2], ctx->ev[3]);
     op->times[0] = wfn->hash_seconds;
     op->times[1] = ms01 * 1e-3;
     op->times[2] = ms12 * 1e-3;
@@ -595,7 +829,7 @@ int wfn_build_index(pyci_wfn *wfn) {
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "too many determinants for the device index (%ld)", wfn->ndet);
     wfn->mask = (u32)(cap - 1);
     const size_t bytes = slot_bytes(wfn->keymode) * (size_t)cap;
-    PYCI_CUDA(cudaMalloc(&wfn->slots, bytes));
+    PYCI_CUDA(dev_malloc(&wfn->slots, bytes));
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     PYCI_CUDA(cudaMemsetAsync(wfn->slots, 0xFF, bytes, ctx->stream));
     int rc;
@@ -669,7 +903,7 @@ int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_
     // SparseOp::size in the reference's storage
     if (op->symmetric) {
         unsigned long long *acc = nullptr;
-        PYCI_CUDA(cudaMalloc(&acc, sizeof(unsigned long long)));
+        PYCI_CUDA(dev_malloc(&acc, sizeof(unsigned long long)));
         PYCI_CUDA(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), ctx->stream));
         if (op->nloc > 0) {
             lowcnt_sum_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(op->lowcnt, op->nloc, acc);
@@ -678,7 +912,7 @@ int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_
         unsigned long long h = 0;
         PYCI_CUDA(cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(acc);
+        dev_free(acc);
         op->size_ref = (long)h;
     } else {
         op->size_ref = op->nnz;

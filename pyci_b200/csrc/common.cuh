@@ -100,11 +100,23 @@ struct pyci_op {
     int *lowcnt = nullptr;   // [nloc] entries with col <= row (sorted rows => a prefix)
     double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
     double times[4] = {0, 0, 0, 0};
+    int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use
     // scratch for host-facing matvec
     double *xbuf = nullptr, *ybuf = nullptr;
 };
 
+// Makes ctx's device current and its stream the target of dev_malloc / dev_free on this thread.
 int ctx_activate(const pyci_ctx *ctx);
+
+// Stream-ordered device allocation from the device's default memory pool (cudaMallocAsync on the active
+// context's stream).  pyci_ctx_create raises the pool's release threshold, so the multi-GB CSR buffers of
+// a destroyed operator are reused by the next build instead of going back to the driver.
+cudaStream_t dev_current_stream();
+template<class T>
+inline cudaError_t dev_malloc(T **p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes, dev_current_stream());
+}
+inline cudaError_t dev_free(void *p) { return p ? cudaFreeAsync(p, dev_current_stream()) : cudaSuccess; }
 
 // nccl (loaded lazily with dlopen; see comm.cpp)
 int comm_unique_id(void *out128);

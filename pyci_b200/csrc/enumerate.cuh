@@ -9,6 +9,21 @@ namespace {
 
 enum { T_AB = 0, T_AA = 1, T_BB = 2, T_SA = 3, T_SB = 4, T_DIAG = 5, T_PAIR = 6 };
 
+// division of a 31-bit candidate index by a launch-time constant: q = (umulhi(c, mul) + c) >> sh
+struct FastDiv {
+    u32 d, mul, sh;
+};
+inline FastDiv make_fastdiv(u32 d) {
+    FastDiv f;
+    f.d = d ? d : 1;
+    u32 s = 0;
+    while ((1ULL << s) < f.d)
+        ++s;
+    f.sh = s;
+    f.mul = (u32)((((1ULL << 32) * ((1ULL << s) - f.d)) / f.d) + 1ULL);
+    return f;
+}
+
 struct BuildParams {
     const u64 *dets;
     int nwords;
@@ -27,7 +42,13 @@ struct BuildParams {
     int npairs_dim;
     const double *coeffs; // RDMs only
     double *rdm1, *rdm2;  // RDMs only
+    FastDiv dSb, dPva, dPvb, dVa, dVb; // divisors of decode: nSb, nPva, nPvb, nvir_a, nvir_b
+    int sort_passes, sort_dbits;       // LSD radix sort of a row: passes x digit bits cover the column index
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 fdiv(u32 c, const FastDiv &f) { return (__umulhi(c, f.mul) + c) >> f.sh; }
+#endif
 
 __device__ __forceinline__ u32 pack_code(int type, int i, int a, int k, int l) {
     return ((u32)type << 24) | ((u32)i << 18) | ((u32)a << 12) | ((u32)k << 6) | (u32)l;
@@ -210,6 +231,11 @@ inline int enum_params_init(BuildParams &P, const pyci_wfn *wfn) {
     if (P.nSb == 0) { P.nSb = 1; P.nAB = 0; }
     if (P.nvir_a == 0) P.nvir_a = 1;
     if (P.nvir_b == 0) P.nvir_b = 1;
+    P.dSb = make_fastdiv(P.nSb);
+    P.dPva = make_fastdiv(P.nPva);
+    P.dPvb = make_fastdiv(P.nPvb);
+    P.dVa = make_fastdiv((u32)P.nvir_a);
+    P.dVb = make_fastdiv((u32)P.nvir_b);
     return PYCI_OK;
 }
 

@@ -213,10 +213,10 @@ int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *
     P.nloc = std::min(ndet, per * (ctx->rank + 1)) - P.row0;
     P.ncol = ndet;
     double *dc = nullptr, *d12 = nullptr;
-    PYCI_CUDA(cudaMalloc(&dc, sizeof(double) * (size_t)std::max<long>(ndet, 1)));
-    cudaError_t e = cudaMalloc(&d12, sizeof(double) * (s1 + s2));
+    PYCI_CUDA(dev_malloc(&dc, sizeof(double) * (size_t)std::max<long>(ndet, 1)));
+    cudaError_t e = dev_malloc(&d12, sizeof(double) * (s1 + s2));
     if (e != cudaSuccess) {
-        cudaFree(dc);
+        dev_free(dc);
         PYCI_CUDA(e);
     }
     int rc = PYCI_OK;
@@ -239,7 +239,7 @@ int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *
         return PYCI_OK;
     };
     rc = body();
-    cudaFree(dc);
-    cudaFree(d12);
+    dev_free(dc);
+    dev_free(d12);
     return rc;
 }

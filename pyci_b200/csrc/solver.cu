@@ -198,13 +198,13 @@ struct Solver {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 
     ~Solver() {
-        cudaFree(V);
-        cudaFree(W);
-        cudaFree(X);
-        cudaFree(AX);
-        cudaFree(T);
-        cudaFree(xfull);
-        cudaFree(dsmall);
+        dev_free(V);
+        dev_free(W);
+        dev_free(X);
+        dev_free(AX);
+        dev_free(T);
+        dev_free(xfull);
+        dev_free(dsmall);
         if (hsmall)
             cudaFreeHost(hsmall);
         if (e0)
@@ -312,18 +312,18 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     S.small_cap = std::max(mmax + nroot, 64);
     std::memset(&S.stats, 0, sizeof(S.stats));
     const size_t vec = sizeof(double) * (size_t)S.ld;
-    PYCI_CUDA(cudaMalloc(&S.V, vec * mmax));
-    PYCI_CUDA(cudaMalloc(&S.W, vec * mmax));
-    PYCI_CUDA(cudaMalloc(&S.X, vec * nroot));
-    PYCI_CUDA(cudaMalloc(&S.AX, vec * nroot));
-    PYCI_CUDA(cudaMalloc(&S.T, vec * nroot));
+    PYCI_CUDA(dev_malloc(&S.V, vec * mmax));
+    PYCI_CUDA(dev_malloc(&S.W, vec * mmax));
+    PYCI_CUDA(dev_malloc(&S.X, vec * nroot));
+    PYCI_CUDA(dev_malloc(&S.AX, vec * nroot));
+    PYCI_CUDA(dev_malloc(&S.T, vec * nroot));
     PYCI_CUDA(cudaMemsetAsync(S.V, 0, vec * mmax, S.st));
     PYCI_CUDA(cudaMemsetAsync(S.W, 0, vec * mmax, S.st));
     PYCI_CUDA(cudaMemsetAsync(S.X, 0, vec * nroot, S.st));
     PYCI_CUDA(cudaMemsetAsync(S.AX, 0, vec * nroot, S.st));
     PYCI_CUDA(cudaMemsetAsync(S.T, 0, vec * nroot, S.st));
-    PYCI_CUDA(cudaMalloc(&S.xfull, vec * R));
-    PYCI_CUDA(cudaMalloc(&S.dsmall, sizeof(double) * S.small_cap));
+    PYCI_CUDA(dev_malloc(&S.xfull, vec * R));
+    PYCI_CUDA(dev_malloc(&S.dsmall, sizeof(double) * S.small_cap));
     PYCI_CUDA(cudaMallocHost(&S.hsmall, sizeof(double) * S.small_cap));
     PYCI_CUDA(cudaEventCreate(&S.e0));
     PYCI_CUDA(cudaEventCreate(&S.e1));
