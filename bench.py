@@ -442,7 +442,7 @@ def run_b200(args, spec, rank, world, local):
         "roofline": {"kernel": "spmv_rows", "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
                      "frac": spmv_gbs / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": int(spmv_bytes), "ms_per_launch": spmv_ms},
-        "roofline_build": {"kernel": "fill_kernel", "bound": "hbm", "achieved": fill_gbs, "peak": peak, "unit": "GB/s",
+        "roofline_build": {"kernel": "fill_sorted_kernel (sorted two-spin wfn) | fill_kernel", "bound": "hbm", "achieved": fill_gbs, "peak": peak, "unit": "GB/s",
                            "frac": fill_gbs / peak, "traffic": None, "bytes_per_launch": int(fill_bytes),
                            "ms_per_launch": 1e3 * fill_s,
                            "note": "issue/latency-bound (hash probes + in-CTA sort), not HBM-bound; see DESIGN.md"},

@@ -13,6 +13,7 @@
 //             streamed to HBM with coalesced stores.
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "enumerate.cuh"
 
@@ -482,6 +483,12 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
     }
 }
 
+} // namespace
+
+#include "build_sorted.cuh"
+
+namespace {
+
 // ---- int64 exclusive scan of the row counts -------------------------------------------------------
 constexpr int SCAN_BLOCK = 1024;
 
@@ -642,6 +649,15 @@ __global__ void lookup_kernel(DetIndex<KM> ix, const u64 *dets, int nwords, long
     out[i] = ix.find(a, b);
 }
 
+__global__ void sorted_check_kernel(const u64 *dets, long ndet, int *unsorted) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= ndet)
+        return;
+    const u64 a0 = dets[2 * i], b0 = dets[2 * i + 1], a1 = dets[2 * i + 2], b1 = dets[2 * i + 3];
+    if (!(a0 < a1 || (a0 == a1 && b0 < b1)))
+        atomicOr(unsorted, 1);
+}
+
 size_t slot_bytes(int km) { return km == KEY32 ? sizeof(Slot32) : km == KEY64 ? sizeof(Slot64) : sizeof(Slot128); }
 
 template<int KM>
@@ -759,25 +775,73 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     if (nloc > 0 && nnz > 0) {
         diag_kernel<KIND><<<(unsigned)((nloc + 127) / 128), 128, 0, st>>>(P);
         ctx->launches++;
-        int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
-        size_t smem = 0;
-        for (;;) { // keys (ping-pong) + values + radix counters + tables + pair table
-            smem = (size_t)24 * P.maxrow + sizeof(u32) * ((size_t)(block / 32) + 1) * (1u << P.sort_dbits) + tab_bytes +
-                   pair_bytes;
-            if ((long)smem <= (long)ctx->smem_optin || block == 32)
-                break;
-            block >>= 1;
+        bool done = false;
+        if constexpr (KIND == PYCI_FULLCI) {
+            // sorted two-spin wave function: slots in sorted order from two per-row rank lists (build_sorted.cuh)
+            const double Ua = binom_d(P.n, P.nocc_a), Ub = binom_d(P.n, P.nocc_b);
+            if (wfn->sorted2 && P.nocc_a > 0 && P.nocc_b > 0 && P.nvir_a > 0 && P.nvir_b > 0 && P.nAB > 0 &&
+                Ua <= 65536.0 && Ub <= 65536.0 && !getenv("PYCI_B200_NO_SORTED_PATH")) {
+                SortedParams S;
+                S.La = 1 + P.nSa + P.nDa;
+                S.Lb = 1 + P.nSb + P.nDb;
+                S.Wa = ((u32)Ua + 31) / 32;
+                S.Wb = ((u32)Ub + 31) / 32;
+                S.K1 = (u32)std::max(P.nocc_a, P.nocc_b) + 1;
+                S.M = P.ncand + 1;
+                std::vector<u32> hb((size_t)P.n * S.K1);
+                for (int pp = 0; pp < P.n; ++pp)
+                    for (u32 j = 0; j < S.K1; ++j)
+                        hb[(size_t)pp * S.K1 + j] = (u32)std::min(binom_d(pp, j), 4294967295.0);
+                u32 *dbinom = nullptr;
+                PYCI_CUDA(dev_malloc(&dbinom, sizeof(u32) * hb.size()));
+                PYCI_CUDA(cudaMemcpyAsync(dbinom, hb.data(), sizeof(u32) * hb.size(), cudaMemcpyHostToDevice, st));
+                S.binom = dbinom;
+                const int block = pick_block((long)P.ncand / 4);
+                const bool direct = analytic;
+                const size_t smem = sorted_smem_bytes(S, nSa, nSb, (u32)P.n, direct, pair_bytes);
+                if ((long)smem <= (long)ctx->smem_optin) {
+                    int per_sm = 1;
+                    long grid;
+                    if (direct) {
+                        PYCI_CUDA(cudaFuncSetAttribute(fill_sorted_kernel<KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sorted_kernel<KM, true>, block, smem));
+                        grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
+                        fill_sorted_kernel<KM, true><<<(unsigned)grid, block, smem, st>>>(P, ix, S, nSa, nSb);
+                    } else {
+                        PYCI_CUDA(cudaFuncSetAttribute(fill_sorted_kernel<KM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sorted_kernel<KM, false>, block, smem));
+                        grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
+                        fill_sorted_kernel<KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, S, nSa, nSb);
+                    }
+                    ctx->launches++;
+                    done = true;
+                }
+                // hb stays alive until the copy is consumed: the stream is synchronised below
+                PYCI_CUDA(cudaStreamSynchronize(st));
+                dev_free(dbinom);
+            }
         }
-        if ((long)smem > (long)ctx->smem_optin)
-            PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
-                      "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
-                      maxrow, (long)((ctx->smem_optin - tab_bytes - pair_bytes - 2048) / 24));
-        PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM>, block, smem));
-        const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-        fill_kernel<KIND, KM><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
-        ctx->launches++;
+        if (!done) {
+            int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
+            size_t smem = 0;
+            for (;;) { // keys (ping-pong) + values + radix counters + tables + pair table
+                smem = (size_t)24 * P.maxrow + sizeof(u32) * ((size_t)(block / 32) + 1) * (1u << P.sort_dbits) +
+                       tab_bytes + pair_bytes;
+                if ((long)smem <= (long)ctx->smem_optin || block == 32)
+                    break;
+                block >>= 1;
+            }
+            if ((long)smem > (long)ctx->smem_optin)
+                PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
+                          "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
+                          maxrow, (long)((ctx->smem_optin - tab_bytes - pair_bytes - 2048) / 24));
+            PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM>, block, smem));
+            const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
+            fill_kernel<KIND, KM><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+            ctx->launches++;
+        }
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[3], st));
     PYCI_CUDA(cudaStreamSynchronize(st));
@@ -845,6 +909,18 @@ int wfn_build_index(pyci_wfn *wfn) {
         break;
     }
     PYCI_TRY(rc);
+    wfn->sorted2 = false;
+    if (wfn->kind == PYCI_FULLCI && wfn->ndet > 0) {
+        int *flag = nullptr, h = 1;
+        PYCI_CUDA(dev_malloc(&flag, sizeof(int)));
+        PYCI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+        sorted_check_kernel<<<(unsigned)((wfn->ndet + 255) / 256), 256, 0, ctx->stream>>>(wfn->dets, wfn->ndet, flag);
+        ctx->launches++;
+        PYCI_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(flag);
+        wfn->sorted2 = (h == 0);
+    }
     PYCI_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;

@@ -321,3 +321,35 @@ def test_key_modes(pyci):
     _, one, two = O.synthetic_integrals(40, 5)
     oi, ox, od = O.sparse_op(O.DOCI, 40, 2, 2, wfn.to_det_array(), O.senzero_integrals(one, two))
     assert_csr(op, oi, ox, od)
+
+
+@pytest.mark.parametrize("n,occ", [(9, (3, 3)), (8, (4, 2)), (10, (3, 2)), (7, (1, 1)), (6, (5, 5))])
+def test_fill_paths_sorted_incomplete_unsorted_rectangular(pyci, n, occ):
+    """The three fill strategies give the same CSR as the oracle: sorted complete space (direct slots),
+    sorted incomplete / rectangular (slots + hit compaction), shuffled determinant order (radix sort)."""
+    ecore, one, two = O.synthetic_integrals(n, 99)
+    ham = pyci.hamiltonian(ecore, one, two)
+    full = pyci.fullci_wfn(n, *occ)
+    full.add_all_dets()
+    dets = full.to_det_array()
+    rng = np.random.default_rng(5)
+    keep = np.sort(rng.choice(len(dets), size=max(2, (2 * len(dets)) // 3), replace=False))
+    cases = {
+        "sorted-complete": (dets, {}),
+        "sorted-complete-rect": (dets, dict(nrow=len(dets) - 3, ncol=len(dets) - 5, symmetric=False)),
+        "sorted-incomplete": (dets[keep], {}),
+        "sorted-incomplete-nonsym": (dets[keep], dict(symmetric=False)),
+        "shuffled": (dets[rng.permutation(len(dets))], {}),
+        "shuffled-incomplete": (dets[rng.permutation(keep)], dict(symmetric=False)),
+    }
+    for name, (d, kw) in cases.items():
+        wfn = pyci.fullci_wfn(n, occ[0], occ[1], np.ascontiguousarray(d))
+        op = pyci.sparse_op(ham, wfn, **kw)
+        oi, ox, od = O.sparse_op(O.FULLCI, n, occ[0], occ[1], d, (one, two), **kw)
+        assert np.array_equal(op.indptr(), oi), name
+        assert np.array_equal(op.indices(), ox), name
+        assert np.array_equal(op.data(), od), name
+        x = seeded_vec(op.shape[1], 3)
+        y = op(x)
+        yo = O.matvec(oi, ox, od, x, kw.get("symmetric", True))
+        np.testing.assert_allclose(y, yo, rtol=0, atol=1e-12 * max(1.0, np.abs(yo).max()), err_msg=name)
