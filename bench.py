@@ -64,6 +64,13 @@ def workload_spec(name):
         return dict(kind="fullci", occ=(4, 4), n=14, label="cfg3: FullCI 14 orbitals 4a4b, synthetic integrals seed %d" % SEED)
     if name == "cfg4":
         return dict(kind="fullci", occ=(4, 4), n=16, label="cfg4: FullCI 16 orbitals 4a4b, synthetic integrals seed %d" % SEED)
+    if name == "cfg5":
+        # "K,P,ndet": seniority-zero selection of P pairs in K spatial orbitals as a GenCI space over 2K
+        # spin-orbitals (pyci_b200/synthetic.py); default = 50 M determinants, ~220 stored entries per row
+        K, Pn, nd = (int(v) for v in os.environ.get("PYCI_B200_CFG5", "32,10,50000000").split(","))
+        return dict(kind="genci", occ=(2 * Pn, 0), n=2 * K, cfg5=(K, Pn, nd),
+                    label="cfg5: GenCI %d spin-orbitals %d electrons, %d selected (seniority-zero) determinants, "
+                          "synthetic integrals seed %d" % (2 * K, 2 * Pn, nd, SEED))
     if name.startswith("syn"):
         n = int(name[3:])
         return dict(kind="fullci", occ=(4, 4), n=n, label="FullCI %d orbitals 4a4b, synthetic integrals seed %d" % (n, SEED))
@@ -82,6 +89,14 @@ def _synthetic():
 
 def make_problem(pyci, spec):
     """(ham, wfn) through the public API of `pyci` (this repo's module or the compiled reference)."""
+    if "cfg5" in spec:
+        K, Pn, nd = spec["cfg5"]
+        syn = _synthetic()
+        _, one, two = syn.synthetic_integrals(K, SEED)
+        h_so, g_so = syn.spin_orbital_integrals(one, two)
+        ham = pyci.secondquant_op(0.0, h_so, g_so)
+        wfn = pyci.genci_wfn(2 * K, 2 * Pn, 0, syn.seniority_zero_genci_dets(K, Pn, nd))
+        return ham, wfn
     if "file" in spec:
         ham = pyci.secondquant_op(datafile(spec["file"]))
     else:
@@ -141,15 +156,17 @@ class ClockSampler(threading.Thread):
 # reference arm / cpu baseline: the reference's own C++ (oracle/_ref) or, if absent, the C oracle port
 
 
-def load_reference():
+def load_reference(genci=False):
     """(module, kind): oracle/_ref/pyci_ref = the reference's unmodified sources compiled here by
-    oracle/Makefile ("reference"); else None and the caller uses the oracle port."""
+    oracle/Makefile ("reference"); else None and the caller uses the oracle port.  GenCI uses
+    pyci_ref_gencifix (two loop bounds of sparseop.cpp:453,476 corrected; the stock GenCI kernels are defective)."""
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    if os.path.isdir(os.path.join(ref_dir, "pyci_ref")):
+    name = "pyci_ref_gencifix" if genci else "pyci_ref"
+    if os.path.isdir(os.path.join(ref_dir, name)):
         sys.path.insert(0, ref_dir)
         try:
-            import pyci_ref
-            return pyci_ref, "reference"
+            import importlib
+            return importlib.import_module(name), "reference"
         except ImportError:
             pass
     return None, "port"
@@ -163,7 +180,7 @@ class CpuPath:
 
     def __init__(self, spec):
         self.spec = spec
-        self.mod, self.kind = load_reference()
+        self.mod, self.kind = load_reference(spec["kind"] == "genci")
         if self.mod is not None:
             self.ham, self.wfn = make_problem(self.mod, spec)
             self.ndet = len(self.wfn)
@@ -217,6 +234,8 @@ class CpuPath:
 def ref_size_per_row(spec, ndet):
     """Stored entries per row of the default (symmetric, lower-triangular) operator of a complete space."""
     from math import comb
+    if "cfg5" in spec:
+        return None  # selected space: estimated from the sampled rows
     n = spec.get("n")
     if n is None:
         n = {"be_ccpvdz": 14, "h2o_ccpvdz": 24}[spec["file"]]
@@ -233,7 +252,7 @@ def cpu_sample(spec, seconds):
     cp = CpuPath(spec)
     k = cp.rows_for(seconds)
     t, nnz, ts = cp.build_rows(k)
-    per_row = ref_size_per_row(spec, cp.ndet)
+    per_row = ref_size_per_row(spec, cp.ndet) or ((nnz / k - 1.0) / 2.0 + 1.0)
     return {"value": (k / t) * per_row, "unit": "nnz/s", "cores": 1, "kind": cp.kind,
             "sample": "first %d of %d rows x all columns via sparse_op(nrow=k, symmetric=False), %.1f s; "
                       "rows/s scaled by %.1f stored nnz/row of the default operator; the reference hot path is "
@@ -247,8 +266,11 @@ def run_reference(args, spec, rank, world):
     if rank != 0:
         return 0
     cp = CpuPath(spec)
-    per_row = ref_size_per_row(spec, cp.ndet)
     k = cp.rows_for(4.0)  # ~4 s of host work per step
+    per_row = ref_size_per_row(spec, cp.ndet)
+    if per_row is None:
+        _, nnz0, _ = cp.build_rows(k)
+        per_row = (nnz0 / k - 1.0) / 2.0 + 1.0
     for _ in range(args.warmup):
         cp.build_rows(max(64, k // 8))
     t_total, spmv_t, nnz_total = 0.0, 0.0, 0
@@ -403,7 +425,16 @@ def run_b200(args, spec, rank, world, local):
     tte_dev = max_over_ranks(dwfn_index_seconds(cabi, dwfn) + bt2["total"] + st["seconds"])
     op.close()
     state["op"] = None
-    del evecs
+
+    # ---- 1- and 2-RDM of the ground state through the public API (collective when row-sharded), checked by
+    # the energy identity of the reference's test_compute_rdms (test_routines.py:115-133)
+    barrier()
+    t0 = time.perf_counter()
+    d1, d2 = pyci.compute_rdms(wfn, evecs[0])
+    torch.cuda.synchronize()
+    rdm_wall = max_over_ranks(time.perf_counter() - t0)
+    rdm_err = abs(rdm_energy(pyci, ham, spec, wfn, d1, d2) - float(evals[0])) if rank == 0 else 0.0
+    del evecs, d1, d2
 
     # ---- end to end through the public API, host buffers in, row pointer out
     d2h_bytes = 0
@@ -454,6 +485,8 @@ def run_b200(args, spec, rank, world, local):
         "time_to_e0": {"seconds_device": tte_dev, "seconds_wall": tte_wall, "E0": float(evals[0]), "matvecs": st["matvecs"],
                        "residual": st["residual"], "tol": E_TOL, "solve_seconds": st["seconds"],
                        "spmv_seconds": st["spmv_seconds"]},
+        "rdm": {"seconds_wall": rdm_wall, "energy_identity_abs_error": rdm_err,
+                "call": "pyci_b200.compute_rdms(wfn, c0): wfn upload + index + contraction + tensors back"},
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(spec, args.cpu_seconds)
@@ -466,6 +499,17 @@ def run_b200(args, spec, rank, world, local):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def rdm_energy(pyci, ham, spec, wfn, d1, d2):
+    """E = ecore + sum h gamma + 1/4 sum <pq||rs> Gamma in the spin-orbital basis (test_routines.py:130-133)."""
+    if spec["kind"] == "genci":
+        h2, g2, r1, r2 = ham.one_mo, ham.two_mo, d1, d2
+    else:
+        h2, g2 = _synthetic().spin_orbital_integrals(ham.one_mo, ham.two_mo)
+        r1, r2 = pyci.spinize_rdms(d1, d2)
+    e2 = np.einsum("ijkl,ijkl", g2, r2) - np.einsum("ijlk,ijkl", g2, r2)
+    return ham.ecore + np.einsum("ij,ij", h2, r1) + 0.25 * e2
 
 
 def dwfn_index_seconds(cabi, dwfn):

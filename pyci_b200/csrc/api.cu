@@ -561,9 +561,9 @@ int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
 int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_per_sm) {
     if (!op)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
-    if (threads_per_row != 0 && threads_per_row != 32 && threads_per_row != 64 && threads_per_row != 128 &&
-        threads_per_row != 256)
-        PYCI_FAIL(PYCI_ERR_VALUE, "threads_per_row must be 0 (automatic), 32, 64, 128 or 256");
+    if (threads_per_row != 0 && threads_per_row != 1 && threads_per_row != 32 && threads_per_row != 64 &&
+        threads_per_row != 128 && threads_per_row != 256)
+        PYCI_FAIL(PYCI_ERR_VALUE, "threads_per_row must be 0 (automatic), 1 (short-row kernel), 32, 64, 128 or 256");
     if (ctas_per_sm < 1 || ctas_per_sm > 32)
         PYCI_FAIL(PYCI_ERR_VALUE, "ctas_per_sm must be in [1, 32]");
     op->spmv_tpr = threads_per_row;

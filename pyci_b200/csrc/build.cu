@@ -395,7 +395,9 @@ __device__ u64 *block_radix_sort(u64 *a, u64 *b, int m, int passes, int dbits, u
     return a;
 }
 
-template<int KIND, int KM>
+// LAZY: evaluate the matrix element only for candidates that hit (selected spaces where most excitations
+// leave the wave function); otherwise element loads are issued together with the probes.
+template<int KIND, int KM, bool LAZY>
 __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys A | keys B | values | radix counters | excitation tables | pair table
@@ -441,7 +443,10 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
                 val[u] = 0.0;
                 if (c < P.ncand) {
                     u64 A, B;
-                    candidate<KIND, true>(P, rs, T, pairs, c, A, B, val[u]);
+                    if (LAZY)
+                        candidate<KIND, false>(P, rs, T, pairs, c, A, B, val[u]);
+                    else
+                        candidate<KIND, true>(P, rs, T, pairs, c, A, B, val[u]);
                     hit[u] = index.find(A, B);
                 }
             }
@@ -449,6 +454,10 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
             for (int u = 0; u < UNROLL; ++u) {
                 // warp-aggregated append: one shared atomic per warp per step
                 const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
+                if (LAZY && keep) {
+                    u64 A, B;
+                    candidate<KIND, true>(P, rs, T, pairs, base + u * blockDim.x + threadIdx.x, A, B, val[u]);
+                }
                 const u32 msk = __ballot_sync(0xffffffffu, keep);
                 if (msk) {
                     int slot = 0;
@@ -788,6 +797,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 S.Wb = ((u32)Ub + 31) / 32;
                 S.K1 = (u32)std::max(P.nocc_a, P.nocc_b) + 1;
                 S.M = P.ncand + 1;
+                S.Nb = (u32)Ub;
                 std::vector<u32> hb((size_t)P.n * S.K1);
                 for (int pp = 0; pp < P.n; ++pp)
                     for (u32 j = 0; j < S.K1; ++j)
@@ -797,7 +807,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 PYCI_CUDA(cudaMemcpyAsync(dbinom, hb.data(), sizeof(u32) * hb.size(), cudaMemcpyHostToDevice, st));
                 S.binom = dbinom;
                 const int block = pick_block((long)P.ncand / 4);
-                const bool direct = analytic;
+                // PYCI_B200_FORCE_PROBE: resolve columns through the hash index even in a complete space
+                const bool direct = analytic && !getenv("PYCI_B200_FORCE_PROBE");
                 const size_t smem = sorted_smem_bytes(S, nSa, nSb, (u32)P.n, direct, pair_bytes);
                 if ((long)smem <= (long)ctx->smem_optin) {
                     int per_sm = 1;
@@ -835,11 +846,20 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
                           "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
                           maxrow, (long)((ctx->smem_optin - tab_bytes - pair_bytes - 2048) / 24));
-            PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // most candidates miss (selected space): evaluate elements for hits only
+            const bool lazy = !analytic && (double)nnz < 0.25 * (double)nloc * ((double)P.ncand + 1.0);
             int per_sm = 1;
-            PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM>, block, smem));
-            const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-            fill_kernel<KIND, KM><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+            if (lazy) {
+                PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, true>, block, smem));
+                const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
+                fill_kernel<KIND, KM, true><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+            } else {
+                PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, false>, block, smem));
+                const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
+                fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+            }
             ctx->launches++;
         }
     }

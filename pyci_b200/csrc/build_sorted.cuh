@@ -27,6 +27,7 @@ struct SortedParams {
     u32 Wa, Wb;      // bitmap words: ceil(C(n, nocc_a) / 32), ceil(C(n, nocc_b) / 32)
     u32 K1;          // binomial table row length (max(nocc_a, nocc_b) + 1)
     u32 M;           // candidate slots per row = ncand + 1
+    u32 Nb;          // C(n, nocc_b): column = colex(A') * Nb + colex(B') in a complete sorted space
     const u32 *binom; // device: C(p, j), p < n, j < K1
 };
 
@@ -88,6 +89,8 @@ __host__ __device__ inline size_t sorted_smem_bytes(const SortedParams &S, u32 n
     size_t words = 2 * (size_t)S.Wa + 4 * (size_t)S.Wb + 2 * (size_t)S.La + (size_t)S.Lb + (nSb + 1) + (size_t)n * S.K1;
     if (!direct)
         words += S.M + 2 * (size_t)((S.M + 31) / 32);
+    else
+        words += (size_t)S.La + S.Lb;
     words = (words + 1) & ~(size_t)1;
     size_t bytes = 4 * words + 24 * (size_t)((nSa + 1) & ~1u) + 24 * (size_t)((nSb + 1) & ~1u) + pair_bytes;
     bytes = (bytes + 7) & ~(size_t)7;
@@ -114,10 +117,14 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
     u32 *wend = binom + (u32)P.n * S.K1;
     u32 *scol = wend, *hitmap = wend, *hpref = wend;
     const u32 HW = (S.M + 31) / 32;
+    u32 *crA = wend, *crB = wend; // DIRECT: colex ranks of the list entries (column = crA * Nb + crB)
     if (!DIRECT) {
         hitmap = scol + S.M;
         hpref = hitmap + HW;
         wend = hpref + HW;
+    } else {
+        crB = crA + S.La;
+        wend = crB + S.Lb;
     }
     size_t off = ((size_t)(wend - bmA) + 1) & ~(size_t)1;
     unsigned char *tbase = smem_raw + 4 * off;
@@ -206,12 +213,16 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
         // ---- sorted ranks; group sizes in sorted alpha order
         for (u32 t = threadIdx.x; t < S.La + S.Lb; t += blockDim.x) {
             if (t < S.La) {
+                if (DIRECT)
+                    crA[t] = slotA[t] * S.Nb;
                 const u32 rk = bitmap_rank(bmA, pfA, slotA[t]);
                 slotA[t] = rk;
                 gsz[rk] = (t == 0) ? S.Lb : (t <= nSa) ? (1u + nSb) : 1u;
             } else {
                 const u32 h = t - S.La;
                 const u32 cr = slotB0[h];
+                if (DIRECT)
+                    crB[h] = cr;
                 if (h <= nSb)
                     r1[h] = bitmap_rank(bmB1, pfB1, cr);
                 slotB0[h] = bitmap_rank(bmB, pfB, cr);
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 u32 c = base + u * blockDim.x + threadIdx.x;
+                u32 ga = 0, hb = 0; // list entries (alpha, beta) of the candidate
                 hit[u] = -1;
                 val[u] = 0.0;
                 slot[u] = 0;
@@ -265,6 +277,8 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
                         const int par = ((T.sa_meta[sa] ^ T.sb_meta[sb]) >> 16) & 1;
                         val[u] = apply_sign(__ldg(P.two_mo + (T.sa_off[sa] + T.sb_off[sb])), par);
                         slot[u] = slotA[1 + sa] + r1[1 + sb];
+                        ga = 1 + sa;
+                        hb = 1 + sb;
                     } else if ((c -= P.nAB) < nDa) { // sparseop.cpp:339-358
                         const u32 po = fdiv(c, P.dPva), pv = c - po * P.nPva;
                         const uchar2 o = pairs[po], v = pairs[pv];
@@ -274,6 +288,7 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
                         const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
                         val[u] = apply_sign(x, parity_double(rs.det[0], (int)i, (int)k, (int)a, (int)l));
                         slot[u] = slotA[1 + nSa + c];
+                        ga = 1 + nSa + c;
                     } else if ((c -= nDa) < nDb) { // sparseop.cpp:397-416
                         const u32 po = fdiv(c, P.dPvb), pv = c - po * P.nPvb;
                         const uchar2 o = pairs[po], v = pairs[pv];
@@ -283,17 +298,21 @@ __global__ void __launch_bounds__(256) fill_sorted_kernel(BuildParams P, DetInde
                         const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
                         val[u] = apply_sign(x, parity_double(rs.det[1], (int)i, (int)k, (int)a, (int)l));
                         slot[u] = slotB0[1 + nSb + c];
+                        hb = 1 + nSb + c;
                     } else if ((c -= nDb) < nSa) {
                         A = T.sa_str[c];
                         val[u] = T.sa_val[c];
                         slot[u] = slotA[1 + c] + r1[0];
+                        ga = 1 + c;
                     } else {
                         c -= nSa;
                         B = T.sb_str[c];
                         val[u] = T.sb_val[c];
                         slot[u] = slotB0[1 + c];
+                        hb = 1 + c;
                     }
-                    hit[u] = index.find(A, B);
+                    // complete sorted space: the column IS the colex rank pair (twospinwfn.cpp:195-218), no probe
+                    hit[u] = DIRECT ? (int)(crA[ga] + crB[hb]) : index.find(A, B);
                 }
             }
 #pragma unroll

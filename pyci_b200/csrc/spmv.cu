@@ -37,6 +37,56 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
 
 constexpr int SPMV_BLOCK = 256;
 
+// Short rows (selected CI, DOCI: ~10^2 entries): one warp per row, no register pipeline (a row is only a
+// few trips), 32 registers so that 8 CTAs = 64 warps per SM hide the per-row latency chain
+// (row pointer -> values/columns -> x gathers -> reduction).
+__global__ void __launch_bounds__(SPMV_BLOCK, 8)
+spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
+                const double *__restrict__ x, double *__restrict__ y, long nrows) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * SPMV_BLOCK + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * SPMV_BLOCK) >> 5;
+    for (long r = warp; r < nrows; r += nwarps) {
+        const long start = __ldg(indptr + r), end = __ldg(indptr + r + 1);
+        double acc0 = 0.0, acc1 = 0.0;
+        long p = start;
+        if ((p & 1) && p < end) {
+            if (lane == 0)
+                acc0 = ld_stream_f64(vals + p) * __ldg(x + ld_stream_s32(cols + p));
+            ++p;
+        }
+        const long nvec = (end - p) >> 1;
+        long q = lane;
+        for (; q + 32 < nvec; q += 64) {
+            const double2 v0 = ld_stream_f64x2(vals + p + 2 * q);
+            const int2 c0 = ld_stream_s32x2(cols + p + 2 * q);
+            const double2 v1 = ld_stream_f64x2(vals + p + 2 * (q + 32));
+            const int2 c1 = ld_stream_s32x2(cols + p + 2 * (q + 32));
+            const double x00 = __ldg(x + c0.x), x01 = __ldg(x + c0.y);
+            const double x10 = __ldg(x + c1.x), x11 = __ldg(x + c1.y);
+            acc0 = fma(v0.x, x00, acc0);
+            acc1 = fma(v0.y, x01, acc1);
+            acc0 = fma(v1.x, x10, acc0);
+            acc1 = fma(v1.y, x11, acc1);
+        }
+        if (q < nvec) {
+            const double2 v0 = ld_stream_f64x2(vals + p + 2 * q);
+            const int2 c0 = ld_stream_s32x2(cols + p + 2 * q);
+            acc0 = fma(v0.x, __ldg(x + c0.x), acc0);
+            acc1 = fma(v0.y, __ldg(x + c0.y), acc1);
+        }
+        const long tail = p + 2 * nvec;
+        if (tail < end && lane == 31)
+            acc1 = fma(ld_stream_f64(vals + tail), __ldg(x + ld_stream_s32(cols + tail)), acc1);
+        double acc = acc0 + acc1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0)
+            y[r] = acc;
+    }
+}
+
 // TPR threads (a power of two, 32..256) stream one row; a CTA of 256 threads holds 256/TPR rows at a time.
 // Long rows use more threads per row: fewer rows are in flight, so the set of 2 MB pages being streamed
 // stays small, and every thread still issues two independent 16-byte value loads per trip.
@@ -139,14 +189,24 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
     // threads per row from the mean row length (measured: 64 threads x 4 CTAs/SM is best for rows of ~2000)
     if (op->spmv_tpr == 0) {
         const long avg = op->nnz / std::max<long>(op->nloc, 1);
-        int tpr = avg >= 512 ? 64 : 32;
+        int tpr = avg >= 512 ? 64 : avg >= 320 ? 32 : 1; // 1 = spmv_short_rows
         if (const char *e = getenv("PYCI_B200_SPMV_TPR")) // tuning knob
             tpr = atoi(e);
-        op->spmv_tpr = (tpr == 256 || tpr == 128 || tpr == 64) ? tpr : 32;
+        op->spmv_tpr = (tpr == 256 || tpr == 128 || tpr == 64 || tpr == 1) ? tpr : 32;
+        if (tpr == 1)
+            op->spmv_ctas = 8;
         if (const char *e = getenv("PYCI_B200_SPMV_CTAS"))
             op->spmv_ctas = std::max(1, atoi(e));
     }
     const int tpr = op->spmv_tpr;
+    if (tpr == 1) {
+        const long blocks = (op->nloc * 32 + SPMV_BLOCK - 1) / SPMV_BLOCK;
+        const long g = std::min<long>(blocks, (long)ctx->sm_count * op->spmv_ctas);
+        spmv_short_rows<<<(unsigned)g, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
+        ctx->launches++;
+        PYCI_CUDA(cudaGetLastError());
+        return PYCI_OK;
+    }
     const long rpb = SPMV_BLOCK / tpr;
     const long blocks_needed = (op->nloc + rpb - 1) / rpb;
     // persistent-ish grid: a multiple of the SM count

@@ -33,10 +33,6 @@ agg = collections.defaultdict(lambda: [0, 0, ''])
 stall = collections.Counter()
 done_first = False
 for r in csv.reader(src.splitlines()):
-    if len(r) >= 2 and r[0] == 'Function Name':
-        if done_first:
-            break
-        done_first = True
     if len(r) >= 2 and r[0] == 'File Path':
         cur = r[1].split('/')[-1]
         continue
