@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
 
 } // namespace
 
-#include "build_sorted.cuh"
+#include "build_complete.cuh"
 
 namespace {
 
@@ -705,6 +705,103 @@ double binom_d(long n, long k) {
     return b;
 }
 
+// complete sorted two-spin space: string tables for both spins, then the segment-ordered fill (build_complete.cuh)
+int alloc_string_tables(StringTables &T, u32 N, u32 L, u32 L1, u32 nocc, u32 nS, u32 nD) {
+    T.N = N;
+    T.L = L;
+    T.L1 = L1;
+    T.nocc = nocc;
+    T.nS = nS;
+    T.nD = nD;
+    const size_t e = (size_t)N * L, e1 = (size_t)N * L1, eS = std::max<size_t>((size_t)N * nS, 1),
+                 eD = std::max<size_t>((size_t)N * nD, 1);
+    PYCI_CUDA(dev_malloc(&T.cr, 4 * e));
+    PYCI_CUDA(dev_malloc(&T.dval, 8 * e));
+    PYCI_CUDA(dev_malloc(&T.sub, 8 * e1));
+    PYCI_CUDA(dev_malloc(&T.pos1, 4 * e1));
+    PYCI_CUDA(dev_malloc(&T.terms, 8 * e1 * std::max<u32>(nocc, 1)));
+    PYCI_CUDA(dev_malloc(&T.j1self, 4 * (size_t)N));
+    PYCI_CUDA(dev_malloc(&T.selfj, 4 * (size_t)N));
+    PYCI_CUDA(dev_malloc(&T.s_off, 4 * eS));
+    PYCI_CUDA(dev_malloc(&T.s_aux, 4 * eS));
+    PYCI_CUDA(dev_malloc(&T.s_cr, 4 * eS));
+    PYCI_CUDA(dev_malloc(&T.s_pre, 8 * eS));
+    PYCI_CUDA(dev_malloc(&T.d_off, 4 * eD));
+    PYCI_CUDA(dev_malloc(&T.d_cr, 4 * eD));
+    PYCI_CUDA(dev_malloc(&T.d_val, 8 * eD));
+    PYCI_CUDA(dev_malloc(&T.self_off, 4 * (size_t)N));
+    return PYCI_OK;
+}
+
+void free_string_tables(StringTables &T) {
+    void *ptrs[] = {T.cr, T.dval, T.sub, T.pos1, T.terms, T.j1self, T.selfj, T.s_off, T.s_aux, T.s_cr, T.s_pre,
+                    T.d_off, T.d_cr, T.d_val, T.self_off};
+    for (void *q : ptrs)
+        dev_free(q);
+    memset(&T, 0, sizeof(T));
+}
+
+int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, size_t pair_bytes, int *used) {
+    cudaStream_t st = ctx->stream;
+    *used = 0;
+    const u32 Na = (u32)binom_d(P.n, P.nocc_a), Nb = S.Nb;
+    const u32 L1a = 1 + P.nSa, L1b = 1 + P.nSb;
+    const size_t table_bytes = ((size_t)Na * S.La + (size_t)Nb * S.Lb) * 32 + (size_t)Na * L1a * (32 + 8 * P.nocc_a) +
+                               (size_t)Nb * L1b * (32 + 8 * P.nocc_b);
+    // groups of 256 threads per CTA (one CTA per SM) and whether the two_mo slice of an alpha string fits beside them
+    auto fit = [&](bool sl) {
+        for (int g = 4; g >= 1; --g)
+            if ((long)complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, g, sl).total <= (long)ctx->smem_optin)
+                return g;
+        return 0;
+    };
+    bool with_slice = !getenv("PYCI_B200_NO_SLICE");
+    int groups = with_slice ? fit(true) : 0;
+    if (groups < 2) { // the slice leaves room for fewer than two row buffers: integrals through L1/L2 instead
+        with_slice = false;
+        groups = fit(false);
+    }
+    const size_t tsmem = std::max(string_table_smem(S.Wa, S.La, (u32)P.n, S.K1, pair_bytes),
+                                  string_table_smem(S.Wb, S.Lb, (u32)P.n, S.K1, pair_bytes));
+    if (!groups || S.La > 65535u || S.Lb > 65535u || P.n * P.n >= 4096 || S.M >= (1u << 30) ||
+        table_bytes > ((size_t)4 << 30) || (long)tsmem > (long)ctx->smem_optin)
+        return PYCI_OK; // the general sorted path takes it
+    const size_t fsmem = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice).total;
+    CompleteParams C;
+    memset(&C, 0, sizeof(C));
+    int rc = alloc_string_tables(C.A, Na, S.La, L1a, (u32)P.nocc_a, P.nSa, P.nDa);
+    if (rc == PYCI_OK)
+        rc = alloc_string_tables(C.B, Nb, S.Lb, L1b, (u32)P.nocc_b, P.nSb, P.nDb);
+    if (rc != PYCI_OK) {
+        free_string_tables(C.A);
+        free_string_tables(C.B);
+        return rc;
+    }
+    C.M = S.M;
+    C.Nb = Nb;
+    C.dSb = P.dSb;
+    PYCI_CUDA(cudaFuncSetAttribute(string_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+    string_table_kernel<<<std::min<u32>(Na, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.A, 0, (long)Nb, S.Wa, S.K1, S.binom,
+                                                                               S.Lb, L1b);
+    string_table_kernel<<<std::min<u32>(Nb, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.B, 1, 1L, S.Wb, S.K1, S.binom,
+                                                                               S.La, L1a);
+    ctx->launches += 2;
+    const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
+    if (with_slice) {
+        PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fill_complete_kernel<true><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
+    } else {
+        PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        fill_complete_kernel<false><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
+    }
+    ctx->launches++;
+    PYCI_CUDA(cudaGetLastError());
+    free_string_tables(C.A); // stream-ordered: released after the fill has run
+    free_string_tables(C.B);
+    *used = 1;
+    return PYCI_OK;
+}
+
 template<int KIND, int KM>
 int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, int npairs_dim) {
     cudaStream_t st = ctx->stream;
@@ -810,7 +907,13 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 // PYCI_B200_FORCE_PROBE: resolve columns through the hash index even in a complete space
                 const bool direct = analytic && !getenv("PYCI_B200_FORCE_PROBE");
                 const size_t smem = sorted_smem_bytes(S, nSa, nSb, (u32)P.n, direct, pair_bytes);
-                if ((long)smem <= (long)ctx->smem_optin) {
+                if (direct && !getenv("PYCI_B200_NO_COMPLETE_PATH")) {
+                    // complete space: per-string tables + slot-ordered fill (build_complete.cuh)
+                    int used = 0;
+                    PYCI_TRY(run_complete(ctx, P, S, pair_bytes, &used));
+                    done = used != 0;
+                }
+                if (!done && (long)smem <= (long)ctx->smem_optin) {
                     int per_sm = 1;
                     long grid;
                     if (direct) {
