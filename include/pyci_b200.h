@@ -119,6 +119,9 @@ PYCI_API long pyci_op_stored_nnz(const pyci_op *op);
 PYCI_API double pyci_op_ecore(const pyci_op *op);
 /* device seconds of the last build on this rank: [0] hash index, [1] count+scan, [2] fill+sort, [3] total */
 PYCI_API int pyci_op_build_times(const pyci_op *op, double *seconds4);
+/* name of the CUDA kernel that filled this operator (the dominant kernel of a construction; profiling aid --
+ * the reference has one code path, SparseOp::add_row, sparseop.cpp:220-502) */
+PYCI_API const char *pyci_op_fill_kernel(const pyci_op *op);
 
 /* py_indptr / py_indices / py_data (sparseop.cpp:504-514) for this rank's rows, in the reference's
  * layout: indptr[row_count+1] starting at 0, indices int64, data fp64, each row sorted by column

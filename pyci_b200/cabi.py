@@ -58,6 +58,7 @@ PROTOTYPES = {
     "pyci_op_stored_nnz": (_l, [_vp]),
     "pyci_op_ecore": (_d, [_vp]),
     "pyci_op_build_times": (_i, [_vp, _vp]),
+    "pyci_op_fill_kernel": (ctypes.c_char_p, [_vp]),
     "pyci_op_export_csr": (_i, [_vp, _vp, _vp, _vp]),
     "pyci_op_matvec": (_i, [_vp, _vp, _vp]),
     "pyci_op_matvec_dev": (_i, [_vp, _vp, _vp]),
@@ -200,6 +201,9 @@ class Op:
         t = np.zeros(4)
         check(lib().pyci_op_build_times(self.handle, _ptr(t)))
         return dict(index=t[0], count_scan=t[1], fill_sort=t[2], total=t[3])
+
+    def fill_kernel(self):
+        return lib().pyci_op_fill_kernel(self.handle).decode()
 
     def export_csr(self):
         indptr = np.empty(self.row_count + 1, dtype=np.int64)

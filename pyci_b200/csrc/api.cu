@@ -451,6 +451,8 @@ long pyci_op_size(const pyci_op *op) { return op->size_ref; }
 long pyci_op_stored_nnz(const pyci_op *op) { return op->nnz; }
 double pyci_op_ecore(const pyci_op *op) { return op->ecore; }
 
+const char *pyci_op_fill_kernel(const pyci_op *op) { return op ? op->fill_kernel : "none"; }
+
 int pyci_op_build_times(const pyci_op *op, double *seconds4) {
     for (int i = 0; i < 4; ++i)
         seconds4[i] = op->times[i];

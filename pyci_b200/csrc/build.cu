@@ -912,6 +912,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     int used = 0;
                     PYCI_TRY(run_complete(ctx, P, S, pair_bytes, &used));
                     done = used != 0;
+                    if (done)
+                        op->fill_kernel = "fill_complete_kernel";
                 }
                 if (!done && (long)smem <= (long)ctx->smem_optin) {
                     int per_sm = 1;
@@ -929,6 +931,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     }
                     ctx->launches++;
                     done = true;
+                    op->fill_kernel = "fill_sorted_kernel";
                 }
                 // hb stays alive until the copy is consumed: the stream is synchronised below
                 PYCI_CUDA(cudaStreamSynchronize(st));
@@ -964,6 +967,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
             }
             ctx->launches++;
+            op->fill_kernel = "fill_kernel";
         }
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[3], st));

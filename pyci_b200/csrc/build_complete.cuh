@@ -211,8 +211,17 @@ __device__ __forceinline__ double flip_sign(double x, u32 signbit31) { // signbi
     return __hiloint2double(__double2hiint(x) ^ (int)signbit31, __double2loint(x));
 }
 
-__device__ __forceinline__ void group_barrier(int group) {
-    asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+// Two named barriers per group of 256 threads.  FREE: the row buffer may be overwritten (all eight warps wait;
+// warp 0 gets there after the bulk stores of the previous row have read the buffer).  FULL: the row is
+// complete -- warps 1-7 only arrive and move on to the next row's loads, warp 0 waits and launches the TMA.
+__device__ __forceinline__ void bar_free_sync(int group) {
+    asm volatile("bar.sync %0, 256;" ::"r"(2 * group + 1) : "memory");
+}
+__device__ __forceinline__ void bar_full_sync(int group) {
+    asm volatile("bar.sync %0, 256;" ::"r"(2 * group + 2) : "memory");
+}
+__device__ __forceinline__ void bar_full_arrive(int group) {
+    asm volatile("bar.arrive %0, 256;" ::"r"(2 * group + 2) : "memory");
 }
 
 // One CTA per SM; rows [row0, row0 + nloc) are split into one contiguous range per CTA, so a CTA changes alpha
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = (u32)(P.n * P.n);
     const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
-    uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot | parity << 31 | n^3 i + n a | colex(A') * Nb
+    uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot | parity << 31, colex(A') * Nb, parity << 31 | n^3 i + n a
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
     double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
     double *d_val = s_pre + nSa;
@@ -261,7 +270,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             const u64 Adet = P.dets[2 * ((long)ra * Nb)];
             const size_t bS = (size_t)ra * nSa, bD = (size_t)ra * nDa;
             for (u32 g = threadIdx.x; g < nSa; g += blockDim.x) {
-                s_pack[g] = make_uint4(C.A.s_off[bS + g], C.A.s_aux[bS + g], C.A.s_cr[bS + g] * Nb, 0u);
+                const u32 aux = C.A.s_aux[bS + g];
+                s_pack[g] = make_uint4(C.A.s_off[bS + g] | (aux & 0x80000000u), C.A.s_cr[bS + g] * Nb, aux, 0u);
                 s_pre[g] = C.A.s_pre[bS + g];
             }
             for (u32 d = threadIdx.x; d < nDa; d += blockDim.x) {
@@ -308,9 +318,16 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     dv[q] = __ldg(dvalB + t + 256u * q);
                 }
             u32 ps = 0u, sgn1 = 0u;
-            if (t < L1b) { // beta single t of the sub-list (:382-394): own-spin terms, summed after JA below
+            double tq[4] = {0.0, 0.0, 0.0, 0.0}, diag_r = 0.0;
+            if (t < L1b) { // beta single t of the sub-list (:382-394): position, parity, its first own-spin terms
                 ps = __ldg(C.B.pos1 + rb * L1b + t);
                 sgn1 = __ldg(subB + t).y & 0x80000000u;
+                const double *tb = C.B.terms + (size_t)(rb * L1b + t) * nb;
+#pragma unroll
+                for (u32 q = 0; q < 4; ++q)
+                    if (q < nb)
+                        tq[q] = __ldg(tb + q);
+                diag_r = __ldg(P.diag + r);
             }
             const long out0 = r * (long)M; // complete space: every row holds M entries
             const u32 ov = (u32)out0 & 1u, oc = (u32)out0 & 3u;
@@ -318,9 +335,12 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             double *bval = sval + ov;
             int *bcol = scol + oc;
             // the bulk stores of the previous row must have read the buffer before it is overwritten
-            if (t == 0)
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            group_barrier(group);
+            if (t < 32) {
+                if (t == 0)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            bar_free_sync(group);
             // ---- alpha-beta doubles (sparseop.cpp:318-337)
             if (ab_active) {
                 for (u32 w = w0; w < L1b; w += 256) {
@@ -331,11 +351,12 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     const u32 kl = SLICE ? ((eb.y >> 18) & 0xfffu) : (eb.y & 0x3ffffu);
 #pragma unroll 4
                     for (u32 g = gq; g < nSa; g += GP) {
-                        const uint4 a = s_pack[g];
-                        const double v = SLICE ? slice[g * nn + kl] : __ldg(two_mo + ((a.y & 0x7fffffffu) + kl));
-                        const u32 slot = a.x + w;
-                        bcol[slot] = (int)(a.z + eb.x);
-                        bval[slot] = flip_sign(v, (a.y ^ eb.y) & 0x80000000u);
+                        // SLICE needs the first two words only (8-byte shared load instead of 16)
+                        const uint2 a = *reinterpret_cast<const uint2 *>(s_pack + g);
+                        const double v = SLICE ? slice[g * nn + kl] : __ldg(two_mo + ((s_pack[g].z & 0x7fffffffu) + kl));
+                        const u32 slot = (a.x & 0x7fffffffu) + w;
+                        bcol[slot] = (int)(a.y + eb.x);
+                        bval[slot] = flip_sign(v, (a.x ^ eb.y) & 0x80000000u);
                     }
                 }
             }
@@ -363,12 +384,21 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                 }
                 const u32 slot = self_off + (ps & 0xffffu);
                 if (j1 == j1s) {
-                    bval[slot] = P.diag[r];
+                    bval[slot] = (j1 == t) ? diag_r : P.diag[r];
                 } else {
                     const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
                     double v = JA[ps >> 16];
-                    for (u32 q = 0; q < nb; ++q)
-                        v += __ldg(tb + q);
+                    if (j1 == t) {
+#pragma unroll
+                        for (u32 q = 0; q < 4; ++q)
+                            if (q < nb)
+                                v += tq[q];
+                        for (u32 q = 4; q < nb; ++q)
+                            v += __ldg(tb + q);
+                    } else {
+                        for (u32 q = 0; q < nb; ++q)
+                            v += __ldg(tb + q);
+                    }
                     bval[slot] = flip_sign(v, sgn1);
                 }
             }
@@ -394,18 +424,20 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     for (u64 q = Bdet; q; q &= q - 1) {
                         const u32 kk = (u32)__ffsll((long long)q) - 1u;
                         v += SLICE ? slice[g * nn + kk * (u32)n1 + kk]
-                                   : __ldg(two_mo + (a.y & 0x7fffffffu) + (u32)n2 * kk + kk);
+                                   : __ldg(two_mo + (a.z & 0x7fffffffu) + (u32)n2 * kk + kk);
                     }
-                    const u32 slot = a.x + j1s;
-                    bcol[slot] = (int)(a.z + rb);
-                    bval[slot] = flip_sign(v, a.y & 0x80000000u);
+                    const u32 slot = (a.x & 0x7fffffffu) + j1s;
+                    bcol[slot] = (int)(a.y + rb);
+                    bval[slot] = flip_sign(v, a.x & 0x80000000u);
                 }
             }
             // ---- the finished row goes out as two bulk copies (TMA): 16-byte aligned bodies of the value and
             // column streams; the few entries before / after the aligned bodies by scalar stores
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            group_barrier(group);
-            {
+            if (t >= 32) {
+                bar_full_arrive(group);
+            } else {
+                bar_full_sync(group);
                 const u32 hv = ov, nv = (M - hv) >> 1;                    // values: pairs
                 const u32 hc = min(M, (4u - oc) & 3u), nc = (M - hc) >> 2; // columns: quads
                 if (t == 0) {
@@ -419,15 +451,16 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                                      : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (t >= 32 && t < 32 + hv)
-                    P.vals[out0 + t - 32] = bval[t - 32];
-                if (t >= 64 && t - 64 + hv + 2 * nv < M)
-                    P.vals[out0 + hv + 2 * nv + t - 64] = bval[hv + 2 * nv + t - 64];
-                if (t >= 96 && t - 96 < hc)
-                    P.cols[out0 + t - 96] = bcol[t - 96];
-                if (t >= 128 && t - 128 + hc + 4 * nc < M)
-                    P.cols[out0 + hc + 4 * nc + t - 128] = bcol[hc + 4 * nc + t - 128];
-                if (t == 160)
+                // the few entries before / after the aligned bodies (read before warp 0 frees the buffer again)
+                if (t >= 4 && t < 4 + hv)
+                    P.vals[out0 + t - 4] = bval[t - 4];
+                if (t >= 8 && t - 8 + hv + 2 * nv < M)
+                    P.vals[out0 + hv + 2 * nv + t - 8] = bval[hv + 2 * nv + t - 8];
+                if (t >= 12 && t - 12 < hc)
+                    P.cols[out0 + t - 12] = bcol[t - 12];
+                if (t >= 16 && t < 20 && t - 16 + hc + 4 * nc < M)
+                    P.cols[out0 + hc + 4 * nc + t - 16] = bcol[hc + 4 * nc + t - 16];
+                if (t == 20)
                     P.lowcnt[r] = (int)(self_off + __ldg(C.B.selfj + rb)) + 1; // slots up to and including the diagonal
             }
         }

@@ -101,6 +101,7 @@ struct pyci_op {
     int *lowcnt = nullptr;   // [nloc] entries with col <= row (sorted rows => a prefix)
     double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
     double times[4] = {0, 0, 0, 0};
+    const char *fill_kernel = "none"; // which fill path built this operator
     int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use
     // scratch for host-facing matvec
     double *xbuf = nullptr, *ybuf = nullptr;

@@ -184,6 +184,7 @@ py::dict SparseOp::py_stats() const {
     d["count_seconds"] = t[1];
     d["fill_seconds"] = t[2];
     d["build_seconds"] = t[3];
+    d["fill_kernel"] = std::string(pyci_op_fill_kernel(handle));
     d["stored_nnz"] = pyci_op_stored_nnz(handle);
     d["row_begin"] = pyci_op_row_begin(handle);
     d["row_count"] = pyci_op_row_count(handle);
