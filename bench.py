@@ -414,6 +414,13 @@ def run_b200(args, spec, rank, world, local):
     fill_gbs = fill_bytes / max(fill_s, 1e-9) / 1e9
     fill_name = op.fill_kernel()
     op_rows = op.row_count
+    spmv_name = "spmv_rows" if spmv_bytes / max(op_rows, 1) > 12 * 320 else "spmv_short_rows"
+    traffic = {}
+    try:  # dram bytes per launch from the committed ncu --set full captures (single-GPU workloads only)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(spec.get("key", "") if world == 1 else "", {})
+    except (OSError, ValueError):
+        pass
 
     # ---- time to E0: one more construction + the Davidson solve, device-timed
     barrier()
@@ -475,14 +482,13 @@ def run_b200(args, spec, rank, world, local):
         # the dominant kernel of the timed step (one construction) is the fill kernel; the SpMV kernel that the
         # solve spends its time in is reported beside it
         "roofline": {"kernel": fill_name, "bound": "hbm", "achieved": fill_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": fill_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": fill_gbs / peak, "traffic": traffic.get(fill_name, {}).get("bytes"), "peak_source": peak_src,
                      "bytes_per_launch": int(fill_bytes), "ms_per_launch": 1e3 * fill_s,
                      "share_of_step": fill_s / max(dev_ms * 1e-3 / args.steps, 1e-12),
                      "note": "bytes = CSR written once (12 B per stored non-zero + row pointer) + determinants read once; "
                              "CUDA events around the kernel launches inside the library, on the bench stream"},
-        "roofline_spmv": {"kernel": "spmv_rows" if spmv_bytes / max(op_rows, 1) > 12 * 320 else "spmv_short_rows",
-                          "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
-                          "frac": spmv_gbs / peak, "traffic": None, "peak_source": peak_src,
+        "roofline_spmv": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
+                          "frac": spmv_gbs / peak, "traffic": traffic.get(spmv_name, {}).get("bytes"), "peak_source": peak_src,
                           "bytes_per_launch": int(spmv_bytes), "ms_per_launch": spmv_ms},
         "spmv": {"gbs_per_gpu": spmv_gbs, "gbs_total": spmv_bytes_total / (spmv_ms * 1e-3) / 1e9, "ms": spmv_ms,
                  "bytes_per_nnz": 12, "frac_of_peak": spmv_gbs / peak},
@@ -540,6 +546,7 @@ def main():
     if name == "auto":
         name = "cfg3" if max(world, args.gpus) == 1 else "cfg4"
     spec = workload_spec(name)
+    spec["key"] = name
     if args.impl == "reference":
         return run_reference(args, spec, rank, world)
     if world != args.gpus and rank == 0:
