@@ -97,6 +97,29 @@ PYCI_API double pyci_wfn_index_seconds(const pyci_wfn *wfn);
 /* index_det for a batch of determinants (same layout as dets); out[i] = row index or -1 */
 PYCI_API int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out);
 
+/* number of determinants now in the device wave function, and a copy of determinants [start, start+n) */
+PYCI_API long pyci_wfn_ndet(const pyci_wfn *wfn);
+PYCI_API int pyci_wfn_download_dets(const pyci_wfn *wfn, long start, long n, uint64_t *out);
+
+/* ---- selected CI: add_hci (hci.cpp:238-279) and compute_enpt2 (enpt2.cpp:344-400) ------------------- */
+
+/* One heat-bath iteration: every excitation j of every determinant i with |H_ji| > eps / |coeffs[i]| that is not
+ * yet in wfn is appended to wfn (once) and the index is rebuilt; *n_new = number appended (the return value of
+ * the reference's add_hci).  coeffs[ndet].  The reference appends in the iteration order of its hash map
+ * (twospinwfn.cpp:267-270: unspecified); here the new determinants come in first-encounter order of the
+ * reference's serial loop nest.  Read them back with pyci_wfn_download_dets(wfn, old_ndet, *n_new, ...).
+ * The reference's nthread argument has no meaning on the device.  Collective when row-sharded. */
+PYCI_API int pyci_wfn_add_hci(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double eps,
+                     long *n_new);
+/* Epstein-Nesbet second-order energy: *out = energy + sum_j (sum_i H_ji c_i)^2 / (energy - ecore - H_jj) over the
+ * external determinants j reached with |H_ji| > eps / |c_i| (enpt2.cpp:344-374).  FullCI and GenCI wave
+ * functions; for DOCI the reference converts to FullCI first (enpt2.cpp:376-380) and so must the caller.
+ * nterms (may be NULL) receives the number of external determinants.  Collective when row-sharded. */
+PYCI_API int pyci_compute_enpt2(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double energy,
+                       double eps, double *out, long *nterms);
+/* device seconds of the last add_hci / compute_enpt2 walk over wfn */
+PYCI_API double pyci_wfn_ext_seconds(const pyci_wfn *wfn);
+
 /* ---- sparse operator: SparseOp (sparseop.cpp) --------------------------------------------------- */
 
 /* SparseOp::SparseOp + update (sparseop.cpp:49-71,186-201): rows [0,nrow) x columns [0,ncol) of H

@@ -48,6 +48,12 @@ def lib():
         L.oracle_rdms_genci.argtypes = [ctypes.c_long] * 3 + [ctypes.c_void_p] * 4
         L.oracle_all_dets_onespin.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_void_p]
         L.oracle_all_dets_twospin.argtypes = [ctypes.c_long] * 3 + [ctypes.c_void_p]
+        L.oracle_add_hci.restype = ctypes.c_long
+        L.oracle_add_hci.argtypes = [ctypes.c_int] + [ctypes.c_long] * 4 + [ctypes.c_void_p] * 4 + \
+            [ctypes.c_double, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint64))]
+        L.oracle_enpt2.restype = ctypes.c_int
+        L.oracle_enpt2.argtypes = [ctypes.c_int] + [ctypes.c_long] * 4 + [ctypes.c_void_p] * 4 + \
+            [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]
         L.oracle_binomial.restype = ctypes.c_long
         L.oracle_binomial.argtypes = [ctypes.c_long, ctypes.c_long]
         _LIB = L
@@ -214,6 +220,45 @@ def compute_rdms(kind, nbasis, nocc_up, nocc_dn, dets, coeffs):
     if rc != 0:
         raise MemoryError("oracle rdms failed")
     return out
+
+
+def add_hci(kind, nbasis, nocc_up, nocc_dn, dets, ints, coeffs, eps=1.0e-5):
+    """Restates pyci.add_hci(ham, wfn, coeffs, eps) (hci.cpp:22-279): returns the determinants the reference
+    would append, in its order.  ints = (one_mo, two_mo) for FullCI/GenCI, (h, v, w) for DOCI."""
+    L = lib()
+    dets = np.ascontiguousarray(dets, dtype=np.uint64)
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in ints]
+    out = ctypes.POINTER(ctypes.c_uint64)()
+    n = L.oracle_add_hci(kind, nbasis, nocc_up, nocc_dn, dets.shape[0], _p(dets), _p(a[0]), _p(a[1]), _p(c),
+                         float(eps), ctypes.byref(out))
+    if n < 0:
+        raise MemoryError("oracle_add_hci failed")
+    shape = (n,) + tuple(dets.shape[1:])
+    words = int(np.prod(shape))
+    new = np.ctypeslib.as_array(out, shape=(max(words, 1),))[:words].astype(np.uint64, copy=True).reshape(shape)
+    L.oracle_free(out)
+    return new
+
+
+def compute_enpt2(kind, nbasis, nocc_up, nocc_dn, dets, ints, coeffs, energy, ecore, eps=1.0e-6):
+    """Restates pyci.compute_enpt2(ham, wfn, coeffs, energy, eps) (enpt2.cpp:21-400); ints = (one_mo, two_mo)
+    also for DOCI, which the reference evaluates on the FullCI image of the wave function (enpt2.cpp:376-380).
+    Returns (energy + correction, number of external determinants)."""
+    L = lib()
+    dets = np.ascontiguousarray(dets, dtype=np.uint64)
+    if kind == DOCI:
+        d = dets.reshape(dets.shape[0], 1, -1)
+        dets = np.ascontiguousarray(np.concatenate([d, d], axis=1))
+        kind, nocc_dn = FULLCI, nocc_up
+    c = np.ascontiguousarray(coeffs, dtype=np.float64)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in ints]
+    out, nt = ctypes.c_double(0.0), ctypes.c_long(0)
+    rc = L.oracle_enpt2(kind, nbasis, nocc_up, nocc_dn, dets.shape[0], _p(dets), _p(a[0]), _p(a[1]), _p(c),
+                        float(energy), float(ecore), float(eps), ctypes.byref(out), ctypes.byref(nt))
+    if rc != 0:
+        raise MemoryError("oracle_enpt2 failed")
+    return out.value, nt.value
 
 
 def full_symmetric(indptr, indices, data, n):

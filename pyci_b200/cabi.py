@@ -48,6 +48,11 @@ PROTOTYPES = {
     "pyci_wfn_reindex": (_i, [_vp]),
     "pyci_wfn_index_seconds": (_d, [_vp]),
     "pyci_wfn_index_dets": (_i, [_vp, _l, _vp, _vp]),
+    "pyci_wfn_ndet": (_l, [_vp]),
+    "pyci_wfn_download_dets": (_i, [_vp, _l, _l, _vp]),
+    "pyci_wfn_add_hci": (_i, [_vp, _vp, _vp, _vp, _d, ctypes.POINTER(_l)]),
+    "pyci_compute_enpt2": (_i, [_vp, _vp, _vp, _vp, _d, _d, ctypes.POINTER(_d), ctypes.POINTER(_l)]),
+    "pyci_wfn_ext_seconds": (_d, [_vp]),
     "pyci_op_build": (_i, [_vp, _vp, _vp, _l, _l, _i, _vpp]),
     "pyci_op_destroy": (None, [_vp]),
     "pyci_op_nrow": (_l, [_vp]),
@@ -160,6 +165,8 @@ class Wfn:
     def __init__(self, ctx, kind, nbasis, nocc_up, nocc_dn, dets):
         dets = np.ascontiguousarray(dets, dtype=np.uint64)
         self.ndet = int(dets.shape[0])
+        self.det_shape = tuple(dets.shape[1:])
+        self.ctx = ctx
         self.handle = ctypes.c_void_p()
         check(lib().pyci_wfn_upload(ctx.handle, kind, nbasis, nocc_up, nocc_dn, self.ndet, _ptr(dets),
                                     ctypes.byref(self.handle)))
@@ -173,6 +180,32 @@ class Wfn:
         out = np.empty(dets.shape[0], dtype=np.int64)
         check(lib().pyci_wfn_index_dets(self.handle, dets.shape[0], _ptr(dets), _ptr(out)))
         return out
+
+    def download_dets(self, start=0, n=None):
+        n = self.ndet - start if n is None else n
+        out = np.empty((n,) + self.det_shape, dtype=np.uint64)
+        check(lib().pyci_wfn_download_dets(self.handle, start, n, _ptr(out)))
+        return out
+
+    def add_hci(self, ham, coeffs, eps=1.0e-5):
+        """pyci.add_hci on the device wave function; returns the appended determinants."""
+        c = _f64(coeffs)
+        nnew = _l(0)
+        old = self.ndet
+        check(lib().pyci_wfn_add_hci(self.ctx.handle, ham.handle, self.handle, _ptr(c), eps, ctypes.byref(nnew)))
+        self.ndet = int(lib().pyci_wfn_ndet(self.handle))
+        return self.download_dets(old, nnew.value)
+
+    def compute_enpt2(self, ham, coeffs, energy, eps=1.0e-5):
+        """pyci.compute_enpt2 (FullCI / GenCI kinds); returns (energy + correction, external determinants)."""
+        c = _f64(coeffs)
+        out, nt = _d(0.0), _l(0)
+        check(lib().pyci_compute_enpt2(self.ctx.handle, ham.handle, self.handle, _ptr(c), energy, eps,
+                                       ctypes.byref(out), ctypes.byref(nt)))
+        return out.value, nt.value
+
+    def ext_seconds(self):
+        return lib().pyci_wfn_ext_seconds(self.handle)
 
     def close(self):
         if self.handle:

@@ -45,6 +45,14 @@ long binom_l(long n, long k) {
     return (long)b;
 }
 
+long full_space_size(int kind, long nbasis, long nocc_up, long nocc_dn) {
+    if (kind != PYCI_FULLCI)
+        return binom_l(nbasis, nocc_up);
+    return (binom_l(nbasis, nocc_up) < (1L << 31) && binom_l(nbasis, nocc_dn) < (1L << 31))
+               ? binom_l(nbasis, nocc_up) * binom_l(nbasis, nocc_dn)
+               : INT64_MAX;
+}
+
 template<class T>
 int upload(T **dst, const T *src, size_t count, cudaStream_t st) {
     PYCI_CUDA(dev_malloc(dst, sizeof(T) * std::max<size_t>(count, 1)));
@@ -309,12 +317,7 @@ int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long noc
         wfn->keymode = (nbasis <= 16) ? KEY32 : (nbasis <= 32) ? KEY64 : KEY128;
     else
         wfn->keymode = (nbasis <= 32) ? KEY32 : KEY64;
-    const long full = (kind == PYCI_FULLCI)
-                          ? ((binom_l(nbasis, nocc_up) < (1L << 31) && binom_l(nbasis, nocc_dn) < (1L << 31))
-                                 ? binom_l(nbasis, nocc_up) * binom_l(nbasis, nocc_dn)
-                                 : INT64_MAX)
-                          : binom_l(nbasis, nocc_up);
-    wfn->complete = (ndet == full); // uniqueness is verified by the index build
+    wfn->complete = (ndet == full_space_size(kind, nbasis, nocc_up, nocc_dn)); // uniqueness: verified by the index build
     int rc = upload(&wfn->dets, (const u64 *)dets, (size_t)ndet * nwords, ctx->stream);
     if (rc == PYCI_OK)
         rc = wfn_build_index(wfn);
@@ -345,6 +348,54 @@ int pyci_wfn_reindex(pyci_wfn *wfn) {
 }
 
 double pyci_wfn_index_seconds(const pyci_wfn *wfn) { return wfn ? wfn->hash_seconds : 0.0; }
+
+long pyci_wfn_ndet(const pyci_wfn *wfn) { return wfn ? wfn->ndet : 0; }
+
+int pyci_wfn_download_dets(const pyci_wfn *wfn, long start, long n, uint64_t *out) {
+    if (!wfn || (n > 0 && !out))
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (start < 0 || n < 0 || start + n > wfn->ndet)
+        PYCI_FAIL(PYCI_ERR_VALUE, "determinant range [%ld, %ld) out of bounds (ndet = %ld)", start, start + n, wfn->ndet);
+    if (n == 0)
+        return PYCI_OK;
+    PYCI_TRY(ctx_activate(wfn->ctx));
+    PYCI_CUDA(cudaMemcpyAsync(out, wfn->dets + start * wfn->nwords, sizeof(u64) * (size_t)(n * wfn->nwords),
+                              cudaMemcpyDeviceToHost, wfn->ctx->stream));
+    PYCI_CUDA(cudaStreamSynchronize(wfn->ctx->stream));
+    return PYCI_OK;
+}
+
+int pyci_wfn_add_hci(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double eps, long *n_new) {
+    if (!ctx || !ham || !wfn || !coeffs || !n_new)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (ham->nbasis != wfn->nbasis)
+        PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian has %ld basis functions, wave function %ld", ham->nbasis, wfn->nbasis);
+    *n_new = 0;
+    if (wfn->ndet == 0)
+        return PYCI_OK;
+    PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(add_hci_impl(ctx, ham, wfn, coeffs, eps, n_new, &wfn->ext_seconds));
+    if (*n_new > 0) {
+        wfn->complete = (wfn->ndet == full_space_size(wfn->kind, wfn->nbasis, wfn->nocc_up, wfn->nocc_dn));
+        PYCI_TRY(wfn_build_index(wfn));
+    }
+    return PYCI_OK;
+}
+
+double pyci_wfn_ext_seconds(const pyci_wfn *wfn) { return wfn ? wfn->ext_seconds : 0.0; }
+
+int pyci_compute_enpt2(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double energy,
+                       double eps, double *out, long *nterms) {
+    if (!ctx || !ham || !wfn || !coeffs || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (ham->nbasis != wfn->nbasis)
+        PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian has %ld basis functions, wave function %ld", ham->nbasis, wfn->nbasis);
+    if (wfn->kind == PYCI_DOCI)
+        PYCI_FAIL(PYCI_ERR_VALUE, "compute_enpt2 of a DOCI wave function runs on its FullCI image (enpt2.cpp:376-380): "
+                                  "upload the determinants as (d, d) FullCI strings");
+    PYCI_TRY(ctx_activate(ctx));
+    return enpt2_impl(ctx, ham, wfn, coeffs, energy, eps, out, nterms, &wfn->ext_seconds);
+}
 
 int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) {
     if (!wfn || (n > 0 && (!dets || !out)))

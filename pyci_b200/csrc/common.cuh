@@ -84,6 +84,7 @@ struct pyci_wfn {
     void *slots = nullptr; // hash slots (layout by keymode)
     u32 mask = 0;          // capacity-1 (capacity is a power of two)
     double hash_seconds = 0.0;
+    double ext_seconds = 0.0; // device seconds of the last add_hci / compute_enpt2 walk over this wfn
 };
 
 struct pyci_op {
@@ -138,6 +139,12 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
                double *evals, double *evecs, pyci_solve_stats *stats);
 // rdm.cu
 int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2);
+
+// hci.cu
+int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double eps, long *n_new,
+                 double *seconds);
+int enpt2_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const double *coeffs, double energy, double eps,
+               double *out, long *nterms, double *seconds);
 
 // ---------------------------------------------------------------------------------------------
 // device primitives

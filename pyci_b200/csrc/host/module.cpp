@@ -169,6 +169,21 @@ PYBIND11_MODULE(_pyci, m) {
           py::arg("wfn"), py::arg("coeffs"));
 
     // ---- pyci_b200 extensions: device context, row sharding, launch accounting
+    // add_hci / compute_enpt2 (binding.cpp:1147-1181, 1344-1375): same overloads, keywords and defaults
+    m.def("add_hci", [](const SQuantOp &h, DOCIWfn &w, const Array<double> c, double eps, long nt) { return py_add_hci(h, w, c, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1,
+          "Add determinants to a wave function by running an iteration of Heat-Bath CI (on the GPU).");
+    m.def("add_hci", [](const SQuantOp &h, FullCIWfn &w, const Array<double> c, double eps, long nt) { return py_add_hci(h, w, c, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1);
+    m.def("add_hci", [](const SQuantOp &h, GenCIWfn &w, const Array<double> c, double eps, long nt) { return py_add_hci(h, w, c, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1);
+    m.def("compute_enpt2", [](const SQuantOp &h, const DOCIWfn &w, const Array<double> c, double e, double eps, long nt) { return py_compute_enpt2(h, w, c, e, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("energy"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1,
+          "Compute the second-order Epstein-Nesbet perturbation theory correction to the energy (on the GPU).");
+    m.def("compute_enpt2", [](const SQuantOp &h, const FullCIWfn &w, const Array<double> c, double e, double eps, long nt) { return py_compute_enpt2(h, w, c, e, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("energy"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1);
+    m.def("compute_enpt2", [](const SQuantOp &h, const GenCIWfn &w, const Array<double> c, double e, double eps, long nt) { return py_compute_enpt2(h, w, c, e, eps, nt); },
+          py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("energy"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1);
     m.def("device_count", []() { return pyci_device_count(); });
     m.def("set_device", [](int device, uintptr_t stream) { set_device_context(device, stream); }, py::arg("device"),
           py::arg("stream") = 0, "Bind this process to a CUDA device (and optionally an existing cudaStream_t).");

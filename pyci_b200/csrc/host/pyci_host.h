@@ -203,5 +203,8 @@ struct SparseOp {
 };
 
 py::tuple py_compute_rdms(const Wfn &wfn, const Array<double> coeffs);
+long py_add_hci(const SQuantOp &ham, Wfn &wfn, const Array<double> coeffs, double eps, long nthread);
+double py_compute_enpt2(const SQuantOp &ham, const Wfn &wfn, const Array<double> coeffs, double energy, double eps,
+                        long nthread);
 
 } // namespace pyci_host

@@ -230,4 +230,59 @@ py::tuple py_compute_rdms(const Wfn &wfn, const Array<double> coeffs) {
     return py::make_tuple(r1, r2);
 }
 
+// py_add_hci (hci.cpp:282-301; binding.cpp:1147-1181): one heat-bath iteration on the device; the selected
+// determinants are read back and appended to the host wave function so that it stays the single owner of
+// the determinant list.  `nthread` is accepted for signature parity and ignored.
+long py_add_hci(const SQuantOp &ham, Wfn &wfn, const Array<double> coeffs, double eps, long) {
+    if ((long)coeffs.size() < wfn.ndet)
+        throw std::invalid_argument("coeffs has fewer elements than the wave function has determinants");
+    if (wfn.ndet == 0)
+        return 0;
+    DeviceHam dham(ham);
+    DeviceWfn dwfn(wfn);
+    const double *cp = coeffs.data();
+    pyci_ctx *ctx = device_context();
+    long nnew = 0;
+    std::vector<ulong> fresh;
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_wfn_add_hci(ctx, dham.h, dwfn.w, cp, eps, &nnew);
+        if (rc == PYCI_OK && nnew > 0) {
+            fresh.resize((size_t)(nnew * wfn.nw));
+            rc = pyci_wfn_download_dets(dwfn.w, wfn.ndet, nnew, reinterpret_cast<uint64_t *>(fresh.data()));
+        }
+    }
+    check(rc);
+    const long before = wfn.ndet;
+    wfn.reserve(before + nnew);
+    for (long i = 0; i < nnew; ++i)
+        wfn.add_det(&fresh[(size_t)(i * wfn.nw)]);
+    return wfn.ndet - before;
+}
+
+// py_compute_enpt2 (enpt2.cpp:382-398; binding.cpp:1344-1375); DOCI goes through its FullCI image like the
+// reference (enpt2.cpp:376-380)
+double py_compute_enpt2(const SQuantOp &ham, const Wfn &wfn, const Array<double> coeffs, double energy, double eps,
+                        long) {
+    if ((long)coeffs.size() < wfn.ndet)
+        throw std::invalid_argument("coeffs has fewer elements than the wave function has determinants");
+    if (wfn.kind() == PYCI_DOCI) {
+        const FullCIWfn image(static_cast<const DOCIWfn &>(wfn));
+        return py_compute_enpt2(ham, image, coeffs, energy, eps, -1);
+    }
+    DeviceHam dham(ham);
+    DeviceWfn dwfn(wfn);
+    const double *cp = coeffs.data();
+    pyci_ctx *ctx = device_context();
+    double out = energy;
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_compute_enpt2(ctx, dham.h, dwfn.w, cp, energy, eps, &out, nullptr);
+    }
+    check(rc);
+    return out;
+}
+
 } // namespace pyci_host

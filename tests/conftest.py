@@ -62,3 +62,22 @@ def genci_golden():
 def digests():
     with open(os.path.join(GOLDEN, "digests.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def hci_golden():
+    with np.load(os.path.join(GOLDEN, "hci.npz")) as f:
+        return {k: f[k] for k in f.files}
+
+
+HCI_CASES = [("be_fullci", "be_ccpvdz", "fullci", (2, 2), 3), ("h6_fullci", "h6_sto_3g", "fullci", (3, 3), 3),
+             ("lih_fullci", "lih_sto6g", "fullci", (2, 2), 3), ("li2_doci", "li2_ccpvdz", "doci", (3, 3), 3),
+             ("be_doci", "be_ccpvdz", "doci", (2, 2), 2)]
+
+
+def sorted_rows(d):
+    """determinant array sorted lexicographically by its words (order-free comparison of determinant sets)"""
+    if d.shape[0] == 0:
+        return d
+    flat = d.reshape(d.shape[0], -1)
+    return d[np.lexsort(flat.T[::-1])]

@@ -381,3 +381,123 @@ def test_config5_style_selected_genci(pyci):
         anti = g2 - g2.transpose(0, 1, 3, 2)
         e = np.einsum("ij,ij", h2, r1) + 0.25 * np.einsum("ijkl,ijkl", anti, r2)
         assert abs(e - es[0]) < 1e-9
+
+
+# ---- add_hci / compute_enpt2 (hci.cpp, enpt2.cpp) ----------------------------------------------------
+from conftest import HCI_CASES, sorted_rows  # noqa: E402
+
+PT2_RTOL = 1e-12  # ENPT2 energy: fp64 atomics sum the external terms in a different order than the hash map
+
+
+@pytest.mark.parametrize("tag,fn,kind,occ,steps", HCI_CASES)
+def test_add_hci_and_enpt2_against_reference_golden(pyci, hci_golden, tag, fn, kind, occ, steps):
+    """Same inputs as the compiled reference's trajectory: the appended SET equals the reference's, the order is
+    the oracle's first-encounter order, the ENPT2 energies match."""
+    ham = pyci.hamiltonian(datafile(fn))
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    n = one.shape[0]
+    ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
+    for it in range(steps):
+        g = {k: hci_golden[f"{tag}.{it}.{k}"] for k in ("dets", "coeffs", "energy", "eps", "enpt2", "enpt2_tight", "new_sorted")}
+        eps, e, c = float(g["eps"]), float(g["energy"]), g["coeffs"]
+        wfn = getattr(pyci, kind + "_wfn")(n, occ[0], occ[1], g["dets"])
+        for key, ee in (("enpt2", eps), ("enpt2_tight", eps * 1e-2)):
+            pt = pyci.compute_enpt2(ham, wfn, c, e, ee)
+            assert abs(pt - float(g[key])) <= PT2_RTOL * abs(float(g[key]))
+        before = len(wfn)
+        nadd = pyci.add_hci(ham, wfn, c, eps=eps)
+        new = wfn.to_det_array()[before:]
+        assert nadd == len(new) == len(g["new_sorted"]) and len(wfn) == before + nadd
+        assert np.array_equal(sorted_rows(new), g["new_sorted"])
+        assert np.array_equal(new, O.add_hci(KIND[kind], n, occ[0], occ[1], g["dets"], ints, c, eps))
+        # the grown wave function is usable: every new determinant is indexed where it was appended
+        for j in (0, nadd // 2, nadd - 1):
+            if nadd:
+                assert wfn.index_det(new[j]) == before + j
+        assert pyci.add_hci(ham, wfn, np.zeros(len(wfn)), eps=eps) == 0  # c_i = 0: eps / |c_i| = inf
+
+
+def test_hci_loop_like_reference_test(pyci):
+    """test_routines.py:435-460 restated (run_hci): HF -> [sparse_op.solve -> add_hci -> op.update]* reaches the
+    FullCI energy of Be cc-pVDZ; the ENPT2 estimate of an intermediate space lies between E_var and E_FCI-ish."""
+    ham = pyci.hamiltonian(datafile("be_ccpvdz"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 2, 2)
+    wfn.add_hartreefock_det()
+    op = pyci.sparse_op(ham, wfn)
+    es, cs = op.solve(n=1, tol=1e-9)
+    sizes = [len(wfn)]
+    pt_mid = None
+    while True:
+        nadd = pyci.add_hci(ham, wfn, cs[0], eps=1.0e-5)
+        if nadd == 0:
+            break
+        op.update(ham, wfn)
+        es, cs = op.solve(n=1, tol=1e-9)
+        sizes.append(len(wfn))
+        if pt_mid is None:
+            pt_mid = (es[0], pyci.compute_enpt2(ham, wfn, cs[0], es[0], 1.0e-6))
+    assert sizes == sorted(sizes) and sizes[-1] > 1000
+    assert abs(es[0] - (-14.617409507)) < 1e-7   # test_routines.py:44 with the eps = 1e-5 truncation
+    assert pt_mid[1] < pt_mid[0]                 # second-order correction is negative
+    assert op.shape == (len(wfn), len(wfn))
+
+
+@pytest.mark.parametrize("n,occ,frac", [(8, (3, 2), 5), (10, (3, 3), 9), (34, (2, 1), 3)])
+def test_hci_enpt2_synthetic_selected_spaces(pyci, n, occ, frac):
+    """Synthetic integrals (every element non-zero), a thinned FullCI space: exact order vs the oracle, ENPT2 to 1e-12,
+    GenCI on spin-orbital integrals gives the image of the FullCI selection.  n = 34 exercises 128-bit two-spin keys."""
+    ecore, one, two = O.synthetic_integrals(n, 4321)
+    ham = pyci.hamiltonian(ecore, one, two)
+    full = pyci.fullci_wfn(n, *occ)
+    full.add_all_dets()
+    fd = np.ascontiguousarray(full.to_det_array()[::frac][:4000])
+    wfn = pyci.fullci_wfn(n, occ[0], occ[1], fd)
+    c = seeded_vec(len(fd), 3)
+    c /= np.linalg.norm(c)
+    eps = 0.02
+    pt = pyci.compute_enpt2(ham, wfn, c, -1.0, eps)
+    pto, nt = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, -1.0, ecore, eps)
+    assert nt > 0 and abs(pt - pto) <= PT2_RTOL * abs(pto)
+    ref_new = O.add_hci(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, eps)
+    nadd = pyci.add_hci(ham, wfn, c, eps=eps)
+    assert nadd == len(ref_new) > 0
+    assert np.array_equal(wfn.to_det_array()[len(fd):], ref_new)
+    if 2 * n <= 64:
+        h2, g2 = O.spin_orbital_integrals(one, two)
+        gd = np.ascontiguousarray((fd[:, 0] | (fd[:, 1] << np.uint64(n))).reshape(-1, 1))
+        wg = pyci.genci_wfn(2 * n, sum(occ), 0, gd)
+        hamg = pyci.hamiltonian(ecore, h2, g2)
+        ptg = pyci.compute_enpt2(hamg, wg, c, -1.0, eps)
+        assert abs(ptg - pto) <= PT2_RTOL * abs(pto)
+        assert pyci.add_hci(hamg, wg, c, eps=eps) == nadd
+        newg = wg.to_det_array()[len(gd):]
+        assert np.array_equal(newg, O.add_hci(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), c, eps))
+        imgs = (ref_new[:, 0] | (ref_new[:, 1] << np.uint64(n))).reshape(-1, 1)
+        assert np.array_equal(sorted_rows(newg), sorted_rows(imgs))
+
+
+def test_hci_table_growth_and_c_abi(pyci):
+    """A walk that overflows the first external table (2^16 slots) is re-run with a larger one; through the C ABI
+    (ctypes) with device-resident handles, as a reference-side binding would call it."""
+    from pyci_b200 import cabi
+    n, occ = 12, (3, 3)
+    ecore, one, two = O.synthetic_integrals(n, 99)
+    ctx = cabi.Context(0)
+    dets = O.all_dets(O.FULLCI, n, *occ)[::40]
+    c = seeded_vec(len(dets), 8)
+    ham = cabi.Ham(ctx, n, ecore, one, two)
+    wfn = cabi.Wfn(ctx, cabi.FULLCI, n, occ[0], occ[1], dets)
+    ref_new = O.add_hci(O.FULLCI, n, occ[0], occ[1], dets, (one, two), c, 1e-4)
+    assert len(ref_new) > 0.6 * 65536  # more than the first table admits
+    pt, nt = wfn.compute_enpt2(ham, c, -5.0, 1e-4)
+    pto, nto = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], dets, (one, two), c, -5.0, ecore, 1e-4)
+    assert nt == nto == len(ref_new) and abs(pt - pto) <= PT2_RTOL * abs(pto)
+    new = wfn.add_hci(ham, c, 1e-4)
+    assert np.array_equal(new, ref_new)
+    assert wfn.ndet == len(dets) + len(ref_new) and wfn.ext_seconds() > 0
+    assert np.array_equal(wfn.index_dets(new[:100]), len(dets) + np.arange(100))
+    with pytest.raises(cabi.PyciError):
+        cabi.Wfn(ctx, cabi.DOCI, n, 3, 3, np.unique(dets[:, 0]).reshape(-1, 1)).compute_enpt2(ham, c, -5.0, 1e-4)  # DOCI: FullCI image only
+    wfn.close()
+    ham.close()
+    ctx.close()

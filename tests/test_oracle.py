@@ -146,3 +146,44 @@ def test_oracle_rdm_energy_identity():
         anti = g2 - g2.transpose(0, 1, 3, 2)
         e = ecore + np.einsum("ij,ij", h2, r1) + 0.25 * np.einsum("ijkl,ijkl", anti, r2)
         assert abs(e - (e0 + ecore)) < 1e-9
+
+
+# ---- add_hci / compute_enpt2 (hci.cpp, enpt2.cpp) ----------------------------------------------------
+from conftest import HCI_CASES, sorted_rows  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,fn,kind,occ,steps", HCI_CASES)
+def test_oracle_hci_enpt2_against_reference(hci_golden, tag, fn, kind, occ, steps):
+    """The C restatement selects the same determinant SET as the compiled reference's add_hci (its append order
+    is hash-map iteration order, unspecified) and reproduces its ENPT2 energies."""
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    n = one.shape[0]
+    ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
+    for it in range(steps):
+        g = {k: hci_golden[f"{tag}.{it}.{k}"] for k in ("dets", "coeffs", "energy", "eps", "enpt2", "enpt2_tight", "new_sorted")}
+        eps, e = float(g["eps"]), float(g["energy"])
+        new = O.add_hci(KIND[kind], n, occ[0], occ[1], g["dets"], ints, g["coeffs"], eps)
+        assert np.array_equal(sorted_rows(new), g["new_sorted"])
+        assert len(new) == 0 or len(np.unique(new.reshape(len(new), -1), axis=0)) == len(new)
+        for key, ee in (("enpt2", eps), ("enpt2_tight", eps * 1e-2)):
+            pt, _ = O.compute_enpt2(KIND[kind], n, occ[0], occ[1], g["dets"], (one, two), g["coeffs"], e, ecore, ee)
+            assert abs(pt - float(g[key])) <= 1e-13 * abs(float(g[key]))
+
+
+def test_oracle_hci_genci_equals_fullci():
+    """GenCI (loops bounded by nvir_up) on spin-orbital integrals selects the images of the FullCI selection and
+    gives the same ENPT2 energy."""
+    ecore, one, two = O.read_fcidump(datafile("h6_sto_3g"))
+    n, occ = one.shape[0], (3, 3)
+    h2, g2 = O.spin_orbital_integrals(one, two)
+    fd = O.all_dets(O.FULLCI, n, *occ)[::7]
+    c = seeded_vec(len(fd), 5)
+    c /= np.linalg.norm(c)
+    gd = (fd[:, 0] | (fd[:, 1] << np.uint64(n))).reshape(-1, 1)
+    newf = O.add_hci(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, 1.0e-3)
+    newg = O.add_hci(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), c, 1.0e-3)
+    assert len(newf) > 0
+    assert np.array_equal(sorted_rows((newf[:, 0] | (newf[:, 1] << np.uint64(n))).reshape(-1, 1)), sorted_rows(newg))
+    ptf, ntf = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, -3.0, ecore, 1.0e-4)
+    ptg, ntg = O.compute_enpt2(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), c, -3.0, ecore, 1.0e-4)
+    assert ntf == ntg and abs(ptf - ptg) <= 1e-12 * abs(ptf)
