@@ -165,6 +165,10 @@ PYCI_API int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_byt
  * the mean row length) and resident CTAs of 256 threads per SM (default 4).  A tuning knob only: results
  * are identical for every shape up to the summation order inside a row. */
 PYCI_API int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_per_sm);
+/* Threads per CTA of the row kernel (256, 512 or 1024): block_threads / threads_per_row consecutive rows are
+ * streamed in lockstep by one CTA and share their gathers of x in L1; depth (2..4) = trips of (value, column)
+ * loads every thread keeps in flight.  Tuning knobs only. */
+PYCI_API int pyci_op_set_spmv_block(pyci_op *op, int block_threads, int depth);
 /* SparseOp::get_element (sparseop.cpp:89-94); i must be a row of this rank */
 PYCI_API int pyci_op_get_element(pyci_op *op, long i, long j, double *out);
 

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "pyci_op_matvec_dev": (_i, [_vp, _vp, _vp]),
     "pyci_op_time_spmv": (_i, [_vp, _i, _i, _l, _vp]),
     "pyci_op_set_spmv_shape": (_i, [_vp, _i, _i]),
+    "pyci_op_set_spmv_block": (_i, [_vp, _i, _i]),
     "pyci_op_get_element": (_i, [_vp, _l, _l, _vp]),
     "pyci_op_solve": (_i, [_vp, _l, _vp, _l, _l, _d, _vp, _vp, ctypes.POINTER(SolveStats)]),
     "pyci_compute_rdms": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -262,6 +263,9 @@ class Op:
 
     def set_spmv_shape(self, threads_per_row=0, ctas_per_sm=4):
         check(lib().pyci_op_set_spmv_shape(self.handle, threads_per_row, ctas_per_sm))
+
+    def set_spmv_block(self, block_threads=256, depth=2):
+        check(lib().pyci_op_set_spmv_block(self.handle, block_threads, depth))
 
     def get_element(self, i, j):
         v = ctypes.c_double(0.0)

@@ -491,6 +491,7 @@ void pyci_op_destroy(pyci_op *op) {
     dev_free(op->diag);
     dev_free(op->xbuf);
     dev_free(op->ybuf);
+    dev_free(op->spmv_part);
     delete op;
 }
 
@@ -615,12 +616,26 @@ int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_per_sm) {
     if (!op)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     if (threads_per_row != 0 && threads_per_row != 1 && threads_per_row != 32 && threads_per_row != 64 &&
-        threads_per_row != 128 && threads_per_row != 256)
-        PYCI_FAIL(PYCI_ERR_VALUE, "threads_per_row must be 0 (automatic), 1 (short-row kernel), 32, 64, 128 or 256");
+        threads_per_row != 128 && threads_per_row != 256 && threads_per_row != -8 && threads_per_row != -16 &&
+        threads_per_row != -24 && threads_per_row != -32)
+        PYCI_FAIL(PYCI_ERR_VALUE, "threads_per_row must be 0 (automatic), 1 (short-row kernel), 32, 64, 128, 256, or "
+                                  "-8/-16/-24/-32 (bulk-copy stream kernel with that many warps per CTA)");
     if (ctas_per_sm < 1 || ctas_per_sm > 32)
         PYCI_FAIL(PYCI_ERR_VALUE, "ctas_per_sm must be in [1, 32]");
     op->spmv_tpr = threads_per_row;
     op->spmv_ctas = ctas_per_sm;
+    return PYCI_OK;
+}
+
+int pyci_op_set_spmv_block(pyci_op *op, int block_threads, int depth) {
+    if (!op)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (block_threads != 256 && block_threads != 512 && block_threads != 1024)
+        PYCI_FAIL(PYCI_ERR_VALUE, "block_threads must be 256, 512 or 1024");
+    if (depth < 2 || depth > 4)
+        PYCI_FAIL(PYCI_ERR_VALUE, "depth must be 2, 3 or 4");
+    op->spmv_block = block_threads;
+    op->spmv_depth = depth;
     return PYCI_OK;
 }
 

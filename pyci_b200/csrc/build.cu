@@ -672,8 +672,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     P.rowcnt = nullptr;
 
     op->nnz = nnz;
-    PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)std::max<long>(nnz, 1)));
-    PYCI_CUDA(dev_malloc(&op->vals, sizeof(double) * (size_t)std::max<long>(nnz, 1)));
+    PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)(nnz + 4))); // +4: 16-byte bulk reads may overrun the end
+    PYCI_CUDA(dev_malloc(&op->vals, sizeof(double) * (size_t)(nnz + 4)));
     P.cols = op->cols;
     P.vals = op->vals;
     P.maxrow = (maxrow + 1) & ~1;

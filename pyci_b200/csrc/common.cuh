@@ -103,7 +103,12 @@ struct pyci_op {
     double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
     double times[4] = {0, 0, 0, 0};
     const char *fill_kernel = "none"; // which fill path built this operator
-    int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use
+    int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use;
+                                     // spmv_tpr < 0: bulk-copy stream kernel with -spmv_tpr warps per CTA, ring depth spmv_ctas
+    int spmv_depth = 2;              // trips of stream loads in flight per thread in spmv_rows (2, 3 or 4)
+    int spmv_block = 256;            // threads per CTA of spmv_rows (256, 512 or 1024)
+    long *spmv_part = nullptr;       // stream kernel: first row of every warp's range [spmv_part_n + 1]
+    int spmv_part_n = 0;
     // scratch for host-facing matvec
     double *xbuf = nullptr, *ybuf = nullptr;
 };

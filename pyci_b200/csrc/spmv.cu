@@ -90,13 +90,14 @@ spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, c
 // TPR threads (a power of two, 32..256) stream one row; a CTA of 256 threads holds 256/TPR rows at a time.
 // Long rows use more threads per row: fewer rows are in flight, so the set of 2 MB pages being streamed
 // stays small, and every thread still issues two independent 16-byte value loads per trip.
-template<int TPR>
-__global__ void __launch_bounds__(SPMV_BLOCK)
+template<int TPR, int BLOCK, int DEPTH>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
 spmv_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
           const double *__restrict__ x, double *__restrict__ y, long nrows) {
-    constexpr int RPB = SPMV_BLOCK / TPR; // rows per block
-    constexpr int WPR = TPR / 32;         // warps per row
-    __shared__ double partial[SPMV_BLOCK / 32];
+    constexpr int RPB = BLOCK / TPR; // rows per block, streamed in lockstep: consecutive rows gather from the same
+                                     // stretches of x at the same time, so their sectors are shared in L1
+    constexpr int WPR = TPR / 32;    // warps per row
+    __shared__ double partial[BLOCK / 32];
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
     for (long base = (long)blockIdx.x * RPB; base < nrows; base += (long)gridDim.x * RPB) {
@@ -114,44 +115,51 @@ spmv_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const d
             const long nvec = (end - p) >> 1; // pairs
             const double *vp = vals + p;
             const int *cp = cols + p;
-            // software pipeline: the (value, column) pairs of trip k+1 are requested before the x gathers of
-            // trip k are waited for, so the HBM stream never drains while a warp sits on its gathers
-            long q = t;
-            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
-            int2 c0 = make_int2(0, 0), c1 = c0;
-            bool h0 = q < nvec, h1 = q + TPR < nvec;
-            if (h0) {
-                v0 = ld_stream_f64x2(vp + 2 * q);
-                c0 = ld_stream_s32x2(cp + 2 * q);
+            // software pipeline, DEPTH trips deep: a trip is two (value pair, column pair) loads per thread; the
+            // trips k+1 .. k+DEPTH-1 are in flight while the x gathers of trip k are waited for, so the HBM stream
+            // never drains while a warp sits on its gathers.  Slots are compile-time indices (no register moves).
+            double2 v[DEPTH][2];
+            int2 c[DEPTH][2];
+            long q = t; // first pair of slot 0's trip
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                const long qd = q + (long)d * 2 * TPR;
+                v[d][0] = v[d][1] = make_double2(0.0, 0.0);
+                c[d][0] = c[d][1] = make_int2(0, 0);
+                if (qd < nvec) {
+                    v[d][0] = ld_stream_f64x2(vp + 2 * qd);
+                    c[d][0] = ld_stream_s32x2(cp + 2 * qd);
+                }
+                if (qd + TPR < nvec) {
+                    v[d][1] = ld_stream_f64x2(vp + 2 * (qd + TPR));
+                    c[d][1] = ld_stream_s32x2(cp + 2 * (qd + TPR));
+                }
             }
-            if (h1) {
-                v1 = ld_stream_f64x2(vp + 2 * (q + TPR));
-                c1 = ld_stream_s32x2(cp + 2 * (q + TPR));
-            }
-            while (h0) {
-                const long qn = q + 2 * TPR;
-                const bool n0 = qn < nvec, n1 = qn + TPR < nvec;
-                double2 w0 = make_double2(0.0, 0.0), w1 = w0;
-                int2 d0 = make_int2(0, 0), d1 = d0;
-                if (n0) {
-                    w0 = ld_stream_f64x2(vp + 2 * qn);
-                    d0 = ld_stream_s32x2(cp + 2 * qn);
+            while (q < nvec) {
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) {
+                    const long qd = q + (long)d * 2 * TPR;
+                    // slots beyond the row's end hold zeros and column 0: their products vanish, no predicate needed
+                    const double x00 = __ldg(x + c[d][0].x), x01 = __ldg(x + c[d][0].y);
+                    const double x10 = __ldg(x + c[d][1].x), x11 = __ldg(x + c[d][1].y);
+                    const double2 u0 = v[d][0], u1 = v[d][1];
+                    const long qn = qd + (long)DEPTH * 2 * TPR; // refill this slot before waiting on the gathers
+                    v[d][0] = v[d][1] = make_double2(0.0, 0.0);
+                    c[d][0] = c[d][1] = make_int2(0, 0);
+                    if (qn < nvec) {
+                        v[d][0] = ld_stream_f64x2(vp + 2 * qn);
+                        c[d][0] = ld_stream_s32x2(cp + 2 * qn);
+                    }
+                    if (qn + TPR < nvec) {
+                        v[d][1] = ld_stream_f64x2(vp + 2 * (qn + TPR));
+                        c[d][1] = ld_stream_s32x2(cp + 2 * (qn + TPR));
+                    }
+                    acc0 = fma(u0.x, x00, acc0);
+                    acc1 = fma(u0.y, x01, acc1);
+                    acc0 = fma(u1.x, x10, acc0);
+                    acc1 = fma(u1.y, x11, acc1);
                 }
-                if (n1) {
-                    w1 = ld_stream_f64x2(vp + 2 * (qn + TPR));
-                    d1 = ld_stream_s32x2(cp + 2 * (qn + TPR));
-                }
-                const double x00 = __ldg(x + c0.x), x01 = __ldg(x + c0.y);
-                acc0 = fma(v0.x, x00, acc0);
-                acc1 = fma(v0.y, x01, acc1);
-                if (h1) {
-                    const double x10 = __ldg(x + c1.x), x11 = __ldg(x + c1.y);
-                    acc0 = fma(v1.x, x10, acc0);
-                    acc1 = fma(v1.y, x11, acc1);
-                }
-                v0 = w0; c0 = d0; v1 = w1; c1 = d1;
-                h0 = n0; h1 = n1;
-                q = qn;
+                q += (long)DEPTH * 2 * TPR;
             }
             const long tail = p + 2 * nvec;
             if (tail < end && t == TPR - 1)
@@ -164,6 +172,8 @@ spmv_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const d
         if (WPR == 1) {
             if (lane == 0 && r < nrows)
                 y[r] = acc;
+            if (BLOCK > 256)
+                __syncthreads(); // keep the rows of a batch in lockstep (L1 sharing of the x gathers)
         } else {
             if (lane == 0)
                 partial[threadIdx.x >> 5] = acc;
@@ -180,25 +190,257 @@ spmv_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const d
     }
 }
 
+
+// ---- bulk-copy (TMA) staged stream ------------------------------------------------------------------
+// Long rows, the Davidson hot loop.  Every warp owns a contiguous range of rows (equal stored entries per warp),
+// i.e. one sequential stream of values and one of columns, and pulls it through a private ring of shared-memory
+// tiles with cp.async.bulk (UBLKCP) completing on an mbarrier: up to ~200 KB per SM are in flight without holding
+// a register, against ~50 KB for register-staged loads at the occupancy the gathers allow.  A lane takes pairs
+// (16-byte value pair + 8-byte column pair, conflict-free), gathers x through the read-only path and keeps a
+// private accumulator for the current row; lanes are reduced once per row, in a fixed order (deterministic).
+// No block-level synchronisation after the ring is set up: producer and consumer of a ring are the same warp.
+constexpr int ST_TW = 256;                     // entries per tile: 2 KB of values + 1 KB of columns
+constexpr int ST_NP = ST_TW / 64;              // pairs per lane per tile
+constexpr int ST_TILE_BYTES = ST_TW * 12;
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n"
+                 "}" ::"r"(bar), "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// part[k] = first row of warp k's range: smallest row whose first entry is at or beyond k/nparts of the stored entries
+__global__ void spmv_partition_kernel(const long *__restrict__ indptr, long nrows, int nparts, long *__restrict__ part) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nparts)
+        return;
+    if (k == nparts) {
+        part[k] = nrows;
+        return;
+    }
+    const long nnz = indptr[nrows];
+    const long target = (long)(((__int128)nnz * k) / nparts);
+    long lo = 0, hi = nrows; // smallest r in [0, nrows] with indptr[r] >= target
+    while (lo < hi) {
+        const long mid = (lo + hi) >> 1;
+        if (indptr[mid] >= target)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    part[k] = lo;
+}
+
+template<int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+spmv_stream(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
+            const double *__restrict__ x, double *__restrict__ y, const long *__restrict__ part, int depth) {
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = st_smem + (size_t)warp * depth * ST_TILE_BYTES;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(st_smem + (size_t)WARPS * depth * ST_TILE_BYTES) + warp * depth;
+    const u32 ring_s = (u32)__cvta_generic_to_shared(ring), bars_s = (u32)__cvta_generic_to_shared(bars);
+    const long gw = (long)blockIdx.x * WARPS + warp;
+    const long r0 = part[gw], r1 = part[gw + 1];
+    if (r0 >= r1)
+        return;
+    const long e0 = __ldg(indptr + r0), e1 = __ldg(indptr + r1);
+    const long base = e0 & ~3L; // tiles start on a 16-byte boundary of the column stream
+    const long ntiles = (e1 - base + ST_TW - 1) / ST_TW;
+    if (lane == 0) {
+        for (int s = 0; s < depth; ++s)
+            mbar_init(bars_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](long t, int s) { // lane 0: request tile t into stage s = t % depth
+        const long lo = base + t * ST_TW;
+        const u32 cnt = (u32)min((long)ST_TW, ((e1 - lo) + 3) & ~3L); // entries, multiple of 4 (arrays are padded)
+        const u32 dst = ring_s + s * ST_TILE_BYTES, bar = bars_s + 8 * s;
+        mbar_expect_tx(bar, cnt * 12u);
+        bulk_g2s(dst, vals + lo, cnt * 8u, bar);
+        bulk_g2s(dst + ST_TW * 8, cols + lo, cnt * 4u, bar);
+    };
+    if (lane == 0)
+        for (int t = 0; t < min((long)depth, ntiles); ++t)
+            issue(t, t);
+
+    long row = r0, pos = e0;
+    long row_end = __ldg(indptr + row + 1);
+    long next_end = (row + 2 <= r1) ? __ldg(indptr + row + 2) : e1; // one row ahead: its latency hides behind a row
+    double acc0 = 0.0, acc1 = 0.0;
+    int s = 0;
+    u32 parity = 0;
+    for (long t = 0; t < ntiles; ++t, ++s) {
+        if (s == depth) {
+            s = 0;
+            parity ^= 1u;
+        }
+        const long lo = base + t * ST_TW, hi = min(lo + ST_TW, e1);
+        mbar_wait(bars_s + 8 * s, parity);
+        const double2 *tv = reinterpret_cast<const double2 *>(ring + s * ST_TILE_BYTES);
+        const int2 *tc = reinterpret_cast<const int2 *>(ring + s * ST_TILE_BYTES + ST_TW * 8);
+        double2 v[ST_NP];
+        int2 c[ST_NP];
+#pragma unroll
+        for (int j = 0; j < ST_NP; ++j) {
+            v[j] = tv[lane + 32 * j];
+            c[j] = tc[lane + 32 * j];
+        }
+        __syncwarp(); // every lane holds its part of the tile: the stage can be refilled
+        if (lane == 0 && t + depth < ntiles)
+            issue(t + depth, s);
+        const int npair = (int)((hi - lo + 1) >> 1); // pairs holding at least one entry below hi
+        double xa[ST_NP], xb[ST_NP];
+#pragma unroll
+        for (int j = 0; j < ST_NP; ++j) {
+            const bool in = lane + 32 * j < npair; // columns beyond the stream's end are not ours to dereference
+            xa[j] = in ? __ldg(x + c[j].x) : 0.0;
+            xb[j] = (in && lo + 2 * (lane + 32 * j) + 1 < hi) ? __ldg(x + c[j].y) : 0.0;
+        }
+        if (pos == lo && row_end >= lo + ST_TW) { // the whole tile lies inside the current row
+#pragma unroll
+            for (int j = 0; j < ST_NP; ++j) {
+                acc0 = fma(v[j].x, xa[j], acc0);
+                acc1 = fma(v[j].y, xb[j], acc1);
+            }
+            pos = lo + ST_TW;
+        } else {
+            for (;;) {
+                while (row < r1 && row_end <= pos) { // finished (or empty) rows
+                    double a = acc0 + acc1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (lane == 0)
+                        y[row] = a;
+                    acc0 = acc1 = 0.0;
+                    ++row;
+                    row_end = next_end;
+                    next_end = (row + 2 <= r1) ? __ldg(indptr + row + 2) : e1;
+                }
+                if (pos >= hi || row >= r1)
+                    break;
+                const long seg_hi = min(row_end, hi);
+                const int a = (int)(pos - lo), b = (int)(seg_hi - lo); // tile-relative entry range of this row
+#pragma unroll
+                for (int j = 0; j < ST_NP; ++j) {
+                    const int e = 2 * (lane + 32 * j);
+                    if (e >= a && e < b)
+                        acc0 = fma(v[j].x, xa[j], acc0);
+                    if (e + 1 >= a && e + 1 < b)
+                        acc1 = fma(v[j].y, xb[j], acc1);
+                }
+                pos = seg_hi;
+            }
+        }
+    }
+    while (row < r1) { // rows that end exactly at the end of the stream (and trailing empty rows)
+        double a = acc0 + acc1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0)
+            y[row] = a;
+        acc0 = acc1 = 0.0;
+        ++row;
+    }
+}
+
+
+template<int WARPS>
+int stream_launch_t(pyci_op *op, const double *x_dev, double *y_dev, int depth) {
+    pyci_ctx *ctx = op->ctx;
+    const size_t smem = (size_t)WARPS * depth * ST_TILE_BYTES + (size_t)WARPS * depth * 8;
+    PYCI_CUDA(cudaFuncSetAttribute(spmv_stream<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spmv_stream<WARPS><<<(unsigned)ctx->sm_count, 32 * WARPS, smem, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev,
+                                                                                 y_dev, op->spmv_part, depth);
+    ctx->launches++;
+    PYCI_CUDA(cudaGetLastError());
+    return PYCI_OK;
+}
+
+int stream_launch(pyci_op *op, const double *x_dev, double *y_dev) {
+    pyci_ctx *ctx = op->ctx;
+    const int warps = -op->spmv_tpr;
+    const int maxdepth = (int)(((long)ctx->smem_optin - 1024) / ((long)warps * (ST_TILE_BYTES + 8)));
+    const int depth = std::max(1, std::min(op->spmv_ctas, maxdepth));
+    const int nparts = ctx->sm_count * warps;
+    if (op->spmv_part_n != nparts) { // row ranges of equal stored entries, one per warp (once per operator and shape)
+        dev_free(op->spmv_part);
+        op->spmv_part = nullptr;
+        PYCI_CUDA(dev_malloc(&op->spmv_part, sizeof(long) * (size_t)(nparts + 1)));
+        spmv_partition_kernel<<<(nparts + 1 + 255) / 256, 256, 0, ctx->stream>>>(op->indptr, op->nloc, nparts, op->spmv_part);
+        ctx->launches++;
+        PYCI_CUDA(cudaGetLastError());
+        op->spmv_part_n = nparts;
+    }
+    switch (warps) {
+    case 8:
+        return stream_launch_t<8>(op, x_dev, y_dev, depth);
+    case 16:
+        return stream_launch_t<16>(op, x_dev, y_dev, depth);
+    case 24:
+        return stream_launch_t<24>(op, x_dev, y_dev, depth);
+    default:
+        return stream_launch_t<32>(op, x_dev, y_dev, depth);
+    }
+}
+
 } // namespace
 
 int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
     pyci_ctx *ctx = op->ctx;
     if (op->nloc <= 0)
         return PYCI_OK;
-    // threads per row from the mean row length (measured: 64 threads x 4 CTAs/SM is best for rows of ~2000)
+    // launch shape from the mean row length.  Measured on cfg3 (rows of 2221, profiles/): one warp per row, 16
+    // consecutive rows in lockstep per CTA of 512 threads, 2 CTAs per SM, 2 trips in flight = 0.95 of the measured
+    // HBM peak; 64 threads per row x 4 CTAs of 256 = 0.91; deeper pipelines spill or lose occupancy.
     if (op->spmv_tpr == 0) {
         const long avg = op->nnz / std::max<long>(op->nloc, 1);
-        int tpr = avg >= 512 ? 64 : avg >= 320 ? 32 : 1; // 1 = spmv_short_rows
-        if (const char *e = getenv("PYCI_B200_SPMV_TPR")) // tuning knob
+        int tpr = avg >= 320 ? 32 : 1; // 1 = spmv_short_rows
+        op->spmv_block = avg >= 512 ? 512 : 256;
+        op->spmv_depth = 2;
+        if (const char *e = getenv("PYCI_B200_SPMV_TPR")) // tuning knobs
             tpr = atoi(e);
-        op->spmv_tpr = (tpr == 256 || tpr == 128 || tpr == 64 || tpr == 1) ? tpr : 32;
+        op->spmv_tpr = (tpr == 256 || tpr == 128 || tpr == 64 || tpr == 1 || tpr == -8 || tpr == -16 || tpr == -24 ||
+                        tpr == -32) ? tpr : 32;
+        if (const char *e = getenv("PYCI_B200_SPMV_DEPTH")) {
+            const int d = atoi(e);
+            if (d >= 2 && d <= 4)
+                op->spmv_depth = d;
+        }
+        if (const char *e = getenv("PYCI_B200_SPMV_BLOCK")) {
+            const int b = atoi(e);
+            if (b == 256 || b == 512 || b == 1024)
+                op->spmv_block = b;
+        }
+        op->spmv_ctas = 1024 / op->spmv_block;
         if (tpr == 1)
             op->spmv_ctas = 8;
+        if (tpr < 0)
+            op->spmv_ctas = (227 * 1024 - 4096) / (-tpr * ST_TILE_BYTES); // deepest ring that fits shared memory
         if (const char *e = getenv("PYCI_B200_SPMV_CTAS"))
             op->spmv_ctas = std::max(1, atoi(e));
     }
     const int tpr = op->spmv_tpr;
+    if (tpr < 0)
+        return stream_launch(op, x_dev, y_dev);
     if (tpr == 1) {
         const long blocks = (op->nloc * 32 + SPMV_BLOCK - 1) / SPMV_BLOCK;
         const long g = std::min<long>(blocks, (long)ctx->sm_count * op->spmv_ctas);
@@ -207,24 +449,34 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
         PYCI_CUDA(cudaGetLastError());
         return PYCI_OK;
     }
-    const long rpb = SPMV_BLOCK / tpr;
+    const int block = op->spmv_block;
+    const long rpb = block / tpr;
     const long blocks_needed = (op->nloc + rpb - 1) / rpb;
     // persistent-ish grid: a multiple of the SM count
     const long grid = std::min<long>(blocks_needed, (long)ctx->sm_count * op->spmv_ctas);
-    switch (tpr) {
-    case 256:
-        spmv_rows<256><<<(unsigned)grid, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
-        break;
-    case 128:
-        spmv_rows<128><<<(unsigned)grid, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
-        break;
-    case 64:
-        spmv_rows<64><<<(unsigned)grid, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
-        break;
-    default:
-        spmv_rows<32><<<(unsigned)grid, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
-        break;
+    static const int carve = getenv("PYCI_B200_SPMV_CARVEOUT") ? atoi(getenv("PYCI_B200_SPMV_CARVEOUT")) : -1;
+    const int depth = op->spmv_depth;
+#define PYCI_SPMV_CASE_D(T, B, D)                                                                                   \
+    if (tpr == T && block == B && depth == D) {                                                                     \
+        if (carve >= 0)                                                                                             \
+            cudaFuncSetAttribute(spmv_rows<T, B, D>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);        \
+        spmv_rows<T, B, D><<<(unsigned)grid, B, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc); \
     }
+#define PYCI_SPMV_CASE(T, B) PYCI_SPMV_CASE_D(T, B, 2) PYCI_SPMV_CASE_D(T, B, 3) PYCI_SPMV_CASE_D(T, B, 4)
+    PYCI_SPMV_CASE(256, 256)
+    PYCI_SPMV_CASE(128, 256)
+    PYCI_SPMV_CASE(64, 256)
+    PYCI_SPMV_CASE(32, 256)
+    PYCI_SPMV_CASE(256, 512)
+    PYCI_SPMV_CASE(128, 512)
+    PYCI_SPMV_CASE(64, 512)
+    PYCI_SPMV_CASE(32, 512)
+    PYCI_SPMV_CASE(256, 1024)
+    PYCI_SPMV_CASE(128, 1024)
+    PYCI_SPMV_CASE(64, 1024)
+    PYCI_SPMV_CASE(32, 1024)
+#undef PYCI_SPMV_CASE
+#undef PYCI_SPMV_CASE_D
     ctx->launches++;
     PYCI_CUDA(cudaGetLastError());
     return PYCI_OK;

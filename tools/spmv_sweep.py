@@ -23,13 +23,16 @@ print(json.dumps(dict(workload=name, build=op.build_times(), nnz=op.stored_nnz))
 byt = op.stored_nnz * 12 + (op.row_count + 1) * 8 + op.row_count * 8 + op.ncol * 8
 x = np.random.default_rng(0).standard_normal(op.ncol)
 yref = None
-for tpr in (32, 64, 128, 256):
-    for ctas in (2, 4, 8):
+shapes = [(64, 4, 256, 2), (64, 4, 256, 3), (32, 2, 512, 2), (32, 2, 512, 3), (32, 2, 512, 4), (32, 1, 1024, 3),
+          (64, 2, 512, 3), (32, 4, 256, 3)]
+for tpr, ctas, blk, depth in shapes:
+    if True:
         op.set_spmv_shape(tpr, ctas)
+        op.set_spmv_block(blk, depth)
         ms = op.time_spmv(3, 10, 0)
         y = op.matvec(x)
         if yref is None:
             yref = y
         err = float(np.max(np.abs(y - yref)) / np.max(np.abs(yref)))
-        print(json.dumps(dict(tpr=tpr, ctas=ctas, ms=float(np.mean(ms)), min_ms=float(ms.min()),
+        print(json.dumps(dict(tpr=tpr, ctas=ctas, block=blk, depth=depth, ms=float(np.mean(ms)), min_ms=float(ms.min()),
                               gbs=byt / (np.mean(ms) * 1e-3) / 1e9, relerr_vs_first=err)), flush=True)
