@@ -296,7 +296,7 @@ def run_reference(args, spec, rank, world):
                  "note": "row-slice CSR product through the same compiled code"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -504,7 +504,7 @@ def run_b200(args, spec, rank, world, local):
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(spec, args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     dwfn.close()
     dham.close()
     ctx.close()
@@ -525,6 +525,25 @@ def rdm_energy(pyci, ham, spec, wfn, d1, d2):
     return ham.ecore + np.einsum("ij,ij", h2, r1) + 0.25 * e2
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout: keep the real stdout for it and send everything else that
+    writes to file descriptor 1 (NCCL's version banner, library chatter) to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dwfn_index_seconds(cabi, dwfn):
     return cabi.lib().pyci_wfn_index_seconds(dwfn.handle)
 
@@ -539,6 +558,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -212,7 +212,21 @@ int pyci_ctx_init_comm(pyci_ctx *ctx, int rank, int nranks, const void *unique_i
         ctx->nranks = 1;
         return PYCI_OK;
     }
-    return comm_init(ctx, rank, nranks, unique_id_128);
+    PYCI_TRY(comm_init(ctx, rank, nranks, unique_id_128));
+    // NCCL sets its channels up lazily, on the first collective of each kind (seconds on an 8-GPU box): pay for it
+    // here, not inside the first solve
+    double *warm = nullptr;
+    const long each = 1L << 17; // 1 MB per rank
+    PYCI_CUDA(dev_malloc(&warm, sizeof(double) * (size_t)each * (size_t)(nranks + 1)));
+    PYCI_CUDA(cudaMemsetAsync(warm, 0, sizeof(double) * (size_t)each * (size_t)(nranks + 1), ctx->stream));
+    int rc = comm_allgather_f64(ctx, warm, warm + each, each);
+    if (rc == PYCI_OK)
+        rc = comm_allreduce_sum_f64(ctx, warm, 64);
+    if (rc == PYCI_OK)
+        rc = comm_allreduce_sum_f64(ctx, warm, each);
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(warm);
+    return rc;
 }
 
 int pyci_ctx_rank(const pyci_ctx *ctx) { return ctx->rank; }

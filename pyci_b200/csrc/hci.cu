@@ -231,15 +231,20 @@ __global__ void iota_kernel(u32 *p, long n) {
         p[i] = (u32)i;
 }
 
-// sum over this rank's share of the external determinants of (sum_i H_ji c_i)^2 / (e0 - H_jj)
+// Sum over this rank's share of the external determinants of (sum_i H_ji c_i)^2 / (e0 - H_jj).  Every rank holds the
+// whole merged list but in its own order (slot placement depends on insertion races), so the share is defined by the
+// determinant itself: rank = hash(j) mod nranks.
 template<int KIND>
 __global__ void __launch_bounds__(256) pt2_reduce_kernel(BuildParams P, const u64 *pay, const u64 *k0, const u64 *k1,
-                                                         long begin, long end, double e0, double *out) {
+                                                         long n, u32 rank, u32 nranks, double e0, double *out) {
     __shared__ double ws[8];
     double acc = 0.0;
-    for (long i = begin + (long)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (long)gridDim.x * blockDim.x) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const u64 a = k0[i], b = (KIND == PYCI_FULLCI) ? k1[i] : 0ULL;
+        if (nranks > 1 && (ext_home(a, b) >> 7) % nranks != rank)
+            continue;
         const double s = __longlong_as_double((long long)pay[i]);
-        const double diag = diag_twobody(P, k0[i], (KIND == PYCI_FULLCI) ? k1[i] : 0ULL);
+        const double diag = diag_twobody(P, a, b);
         acc += s * s / (e0 - diag); // enpt2.cpp:370
     }
     for (int o = 16; o > 0; o >>= 1)
@@ -388,8 +393,100 @@ int walk_kind(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P, const OrderPar
     return walk_key<PYCI_GENCI, MODE>(ctx, wfn, P, O, eps, E, overflowed);
 }
 
-// walk this rank's rows, growing the table until it holds every external determinant; then compact, and when
-// row-sharded gather the lists of all ranks and merge them (every rank ends with the same list)
+// Merge `nlists` dense lists laid out as [nlists][stride] (counts[l] valid entries each) into one list without
+// duplicate determinants: payloads are combined with atomicMin (HCI) or atomicAdd (PT2).
+template<int MODE>
+int merge_lists(pyci_ctx *ctx, bool two, const u64 *pay, const u64 *k0, const u64 *k1, long stride,
+                const std::vector<long> &counts, ExtList &out) {
+    long total = 0;
+    for (long c : counts)
+        total += c;
+    const int nlists = (int)counts.size();
+    const long mcap = std::max<long>(1L << 16, next_pow2(2 * std::max<long>(total, 1)));
+    if (mcap > (1L << 31))
+        PYCI_FAIL(PYCI_ERR_MEMORY, "external-space table would exceed 2^31 slots");
+    long *dcounts = nullptr;
+    ExtBuffers M;
+    auto body = [&]() -> int {
+        PYCI_CUDA(dev_malloc(&dcounts, sizeof(long) * (size_t)nlists));
+        PYCI_CUDA(cudaMemcpyAsync(dcounts, counts.data(), sizeof(long) * (size_t)nlists, cudaMemcpyHostToDevice, ctx->stream));
+        PYCI_TRY(M.rc_alloc(ctx, mcap, two, MODE));
+        const unsigned blocks = (unsigned)std::max<long>(1, std::min<long>((stride + 255) / 256, (long)ctx->sm_count * 8));
+        if (two)
+            ext_merge_kernel<true, MODE><<<blocks, 256, 0, ctx->stream>>>(M.T, pay, k0, k1, stride, nlists, dcounts);
+        else
+            ext_merge_kernel<false, MODE><<<blocks, 256, 0, ctx->stream>>>(M.T, pay, k0, k1, stride, nlists, dcounts);
+        ctx->launches++;
+        PYCI_CUDA(cudaGetLastError());
+        int over = 0;
+        PYCI_CUDA(cudaMemcpyAsync(&over, M.T.overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (over)
+            PYCI_FAIL(PYCI_ERR_RUNTIME, "external-space merge table overflowed");
+        PYCI_TRY(compact(ctx, M, out));
+        return PYCI_OK;
+    };
+    const int rc = body();
+    dev_free(dcounts);
+    M.release();
+    if (rc != PYCI_OK)
+        out.release();
+    return rc;
+}
+
+// Walk rows [row0, row0 + nloc) of the wave function, growing the table until it holds every external
+// determinant they reach, and compact it.
+template<int MODE>
+int walk_rows(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P, const OrderParams &O, double eps, long row0, long nloc,
+              ExtList &out) {
+    P.row0 = row0;
+    P.nloc = nloc;
+    const bool two = wfn->kind == PYCI_FULLCI;
+    long cap = std::max<long>(1L << 16, next_pow2(4 * std::max<long>(nloc, 1)));
+    ExtBuffers E;
+    for (;;) {
+        if (cap > (1L << 31))
+            PYCI_FAIL(PYCI_ERR_MEMORY, "external-space table would exceed 2^31 slots");
+        int rc = E.rc_alloc(ctx, cap, two, MODE);
+        int over = 0;
+        if (rc == PYCI_OK)
+            rc = walk_kind<MODE>(ctx, wfn, P, O, eps, E, &over);
+        if (rc != PYCI_OK) {
+            E.release();
+            return rc;
+        }
+        if (!over)
+            break;
+        E.release();
+        cap *= 4;
+    }
+    const int rc = compact(ctx, E, out);
+    E.release();
+    if (rc != PYCI_OK)
+        out.release();
+    return rc;
+}
+
+// pad lists to a common stride in one [nlists][stride] allocation per word
+int pack_lists(pyci_ctx *ctx, bool two, const std::vector<ExtList> &lists, long stride, u64 **pay, u64 **k0, u64 **k1) {
+    const size_t bytes = sizeof(u64) * (size_t)stride * lists.size();
+    PYCI_CUDA(dev_malloc(pay, bytes));
+    PYCI_CUDA(dev_malloc(k0, bytes));
+    if (two)
+        PYCI_CUDA(dev_malloc(k1, bytes));
+    for (size_t l = 0; l < lists.size(); ++l) {
+        const size_t nb = sizeof(u64) * (size_t)lists[l].n;
+        PYCI_CUDA(cudaMemcpyAsync(*pay + l * stride, lists[l].pay, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        PYCI_CUDA(cudaMemcpyAsync(*k0 + l * stride, lists[l].k0, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (two)
+            PYCI_CUDA(cudaMemcpyAsync(*k1 + l * stride, lists[l].k1, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return PYCI_OK;
+}
+
+// The external space of the whole wave function as one duplicate-free list on every rank.  This rank's rows are
+// walked in `split` consecutive chunks (PYCI_B200_EXT_SPLIT, default 1: bounds the size of one table; the chunks'
+// lists are merged like the ranks' lists), then the per-rank lists are all-gathered and merged.
 template<int MODE>
 int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const double *coeffs_dev, double eps,
                      ExtList &out, double *seconds) {
@@ -413,8 +510,7 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
     }
     const long R = ctx->nranks, ndet = wfn->ndet;
     const long per = (ndet + R - 1) / R;
-    P.row0 = std::min(ndet, per * ctx->rank);
-    P.nloc = std::min(ndet, per * (ctx->rank + 1)) - P.row0;
+    const long my0 = std::min(ndet, per * ctx->rank), myn = std::min(ndet, per * (ctx->rank + 1)) - my0;
     P.ncol = ndet;
     P.one_mo = ham->one_mo;
     P.two_mo = ham->two_mo;
@@ -423,96 +519,72 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
     P.w = ham->w;
     P.coeffs = coeffs_dev;
     const bool two = wfn->kind == PYCI_FULLCI;
+    long split = 1;
+    if (const char *e = getenv("PYCI_B200_EXT_SPLIT"))
+        split = std::max(1L, std::min(64L, atol(e)));
 
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    long cap = std::max<long>(1L << 16, next_pow2(4 * std::max<long>(P.nloc, 1)));
-    ExtBuffers E;
-    for (;;) {
-        if (cap > (1L << 31))
-            PYCI_FAIL(PYCI_ERR_MEMORY, "external-space table would exceed 2^31 slots");
-        int rc = E.rc_alloc(ctx, cap, two, MODE);
-        int over = 0;
-        if (rc == PYCI_OK)
-            rc = walk_kind<MODE>(ctx, wfn, P, O, eps, E, &over);
-        if (rc != PYCI_OK) {
-            E.release();
-            return rc;
-        }
-        if (!over)
-            break;
-        E.release();
-        cap *= 4;
-    }
+    std::vector<ExtList> parts((size_t)split);
     ExtList L;
-    int rc = compact(ctx, E, L);
-    E.release();
+    u64 *gp = nullptr, *g0 = nullptr, *g1 = nullptr, *sp = nullptr, *s0 = nullptr, *s1 = nullptr;
+    auto body = [&]() -> int {
+        const long chunk = (myn + split - 1) / split;
+        std::vector<long> counts;
+        long stride = 1;
+        for (long p = 0; p < split; ++p) {
+            const long lo = std::min(myn, chunk * p), hi = std::min(myn, chunk * (p + 1));
+            PYCI_TRY(walk_rows<MODE>(ctx, wfn, P, O, eps, my0 + lo, hi - lo, parts[(size_t)p]));
+            counts.push_back(parts[(size_t)p].n);
+            stride = std::max(stride, parts[(size_t)p].n);
+        }
+        if (split == 1) {
+            L = parts[0];
+            parts[0] = ExtList();
+        } else {
+            PYCI_TRY(pack_lists(ctx, two, parts, stride, &sp, &s0, &s1));
+            PYCI_TRY(merge_lists<MODE>(ctx, two, sp, s0, s1, stride, counts, L));
+            dev_free(sp);
+            dev_free(s0);
+            dev_free(s1);
+            sp = s0 = s1 = nullptr;
+        }
+        if (R > 1) {
+            std::vector<long> rcounts((size_t)R, 0);
+            rcounts[(size_t)ctx->rank] = L.n;
+            PYCI_TRY(comm_allreduce_sum_i64_host(ctx, rcounts.data(), (int)R));
+            long rstride = 1;
+            for (long c : rcounts)
+                rstride = std::max(rstride, c);
+            std::vector<ExtList> mine(1, L);
+            PYCI_TRY(pack_lists(ctx, two, mine, rstride, &sp, &s0, &s1)); // send buffers padded to the common stride
+            const size_t gb = sizeof(u64) * (size_t)rstride * (size_t)R;
+            PYCI_CUDA(dev_malloc(&gp, gb));
+            PYCI_CUDA(dev_malloc(&g0, gb));
+            PYCI_TRY(comm_allgather_f64(ctx, (const double *)sp, (double *)gp, rstride)); // bit patterns: no arithmetic
+            PYCI_TRY(comm_allgather_f64(ctx, (const double *)s0, (double *)g0, rstride));
+            if (two) {
+                PYCI_CUDA(dev_malloc(&g1, gb));
+                PYCI_TRY(comm_allgather_f64(ctx, (const double *)s1, (double *)g1, rstride));
+            }
+            ExtList G;
+            PYCI_TRY(merge_lists<MODE>(ctx, two, gp, g0, g1, rstride, rcounts, G));
+            L.release();
+            L = G;
+        }
+        return PYCI_OK;
+    };
+    const int rc = body();
+    for (ExtList &q : parts)
+        q.release();
+    dev_free(gp);
+    dev_free(g0);
+    dev_free(g1);
+    dev_free(sp);
+    dev_free(s0);
+    dev_free(s1);
     if (rc != PYCI_OK) {
         L.release();
         return rc;
-    }
-    if (R > 1) {
-        // gather the per-rank lists (padded to the longest) and merge them into one table
-        std::vector<long> counts((size_t)R, 0);
-        counts[(size_t)ctx->rank] = L.n;
-        rc = comm_allreduce_sum_i64_host(ctx, counts.data(), (int)R);
-        long stride = 1, total = 0;
-        for (long c : counts) {
-            stride = std::max(stride, c);
-            total += c;
-        }
-        u64 *gp = nullptr, *g0 = nullptr, *g1 = nullptr, *sp = nullptr, *s0 = nullptr, *s1 = nullptr;
-        long *dcounts = nullptr;
-        ExtBuffers M;
-        ExtList G;
-        auto body = [&]() -> int {
-            PYCI_TRY(rc);
-            const size_t sb = sizeof(u64) * (size_t)stride, gb = sb * (size_t)R;
-            // padded send buffers
-            PYCI_CUDA(dev_malloc(&sp, sb));
-            PYCI_CUDA(dev_malloc(&s0, sb));
-            PYCI_CUDA(cudaMemcpyAsync(sp, L.pay, sizeof(u64) * (size_t)L.n, cudaMemcpyDeviceToDevice, ctx->stream));
-            PYCI_CUDA(cudaMemcpyAsync(s0, L.k0, sizeof(u64) * (size_t)L.n, cudaMemcpyDeviceToDevice, ctx->stream));
-            PYCI_CUDA(dev_malloc(&gp, gb));
-            PYCI_CUDA(dev_malloc(&g0, gb));
-            PYCI_TRY(comm_allgather_f64(ctx, (const double *)sp, (double *)gp, stride)); // bit patterns: no arithmetic
-            PYCI_TRY(comm_allgather_f64(ctx, (const double *)s0, (double *)g0, stride));
-            if (two) {
-                PYCI_CUDA(dev_malloc(&s1, sb));
-                PYCI_CUDA(cudaMemcpyAsync(s1, L.k1, sizeof(u64) * (size_t)L.n, cudaMemcpyDeviceToDevice, ctx->stream));
-                PYCI_CUDA(dev_malloc(&g1, gb));
-                PYCI_TRY(comm_allgather_f64(ctx, (const double *)s1, (double *)g1, stride));
-            }
-            PYCI_CUDA(dev_malloc(&dcounts, sizeof(long) * (size_t)R));
-            PYCI_CUDA(cudaMemcpyAsync(dcounts, counts.data(), sizeof(long) * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
-            const long mcap = std::max<long>(1L << 16, next_pow2(2 * std::max<long>(total, 1)));
-            if (mcap > (1L << 31))
-                PYCI_FAIL(PYCI_ERR_MEMORY, "external-space table would exceed 2^31 slots");
-            PYCI_TRY(M.rc_alloc(ctx, mcap, two, MODE));
-            const unsigned blocks = (unsigned)std::min<long>((stride + 255) / 256, (long)ctx->sm_count * 8);
-            if (two)
-                ext_merge_kernel<true, MODE><<<blocks, 256, 0, ctx->stream>>>(M.T, gp, g0, g1, stride, (int)R, dcounts);
-            else
-                ext_merge_kernel<false, MODE><<<blocks, 256, 0, ctx->stream>>>(M.T, gp, g0, g1, stride, (int)R, dcounts);
-            ctx->launches++;
-            PYCI_CUDA(cudaGetLastError());
-            PYCI_TRY(compact(ctx, M, G));
-            return PYCI_OK;
-        };
-        rc = body();
-        dev_free(gp);
-        dev_free(g0);
-        dev_free(g1);
-        dev_free(sp);
-        dev_free(s0);
-        dev_free(s1);
-        dev_free(dcounts);
-        M.release();
-        L.release();
-        if (rc != PYCI_OK) {
-            G.release();
-            return rc;
-        }
-        L = G;
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -606,17 +678,15 @@ int enpt2_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const do
         PYCI_TRY(enum_params_init(P, wfn));
         P.one_mo = ham->one_mo;
         P.two_mo = ham->two_mo;
-        // every rank holds the merged list: reduce a contiguous share, then sum over ranks
-        const long R = ctx->nranks, per = (L.n + R - 1) / R;
-        const long begin = std::min(L.n, per * ctx->rank), end = std::min(L.n, per * (ctx->rank + 1));
-        if (end > begin) {
-            const unsigned blocks = (unsigned)std::min<long>((end - begin + 255) / 256, (long)ctx->sm_count * 4);
+        // every rank holds the merged list: reduce the determinants this rank owns, then sum over ranks
+        if (L.n > 0) {
+            const unsigned blocks = (unsigned)std::min<long>((L.n + 255) / 256, (long)ctx->sm_count * 4);
             if (wfn->kind == PYCI_FULLCI)
-                pt2_reduce_kernel<PYCI_FULLCI><<<blocks, 256, 0, ctx->stream>>>(P, L.pay, L.k0, L.k1, begin, end,
-                                                                               energy - ham->ecore, acc);
+                pt2_reduce_kernel<PYCI_FULLCI><<<blocks, 256, 0, ctx->stream>>>(P, L.pay, L.k0, L.k1, L.n, (u32)ctx->rank,
+                                                                               (u32)ctx->nranks, energy - ham->ecore, acc);
             else
-                pt2_reduce_kernel<PYCI_GENCI><<<blocks, 256, 0, ctx->stream>>>(P, L.pay, L.k0, L.k1, begin, end,
-                                                                              energy - ham->ecore, acc);
+                pt2_reduce_kernel<PYCI_GENCI><<<blocks, 256, 0, ctx->stream>>>(P, L.pay, L.k0, L.k1, L.n, (u32)ctx->rank,
+                                                                              (u32)ctx->nranks, energy - ham->ecore, acc);
             ctx->launches++;
             PYCI_CUDA(cudaGetLastError());
         }

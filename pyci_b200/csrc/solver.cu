@@ -6,7 +6,9 @@
 // all-reduces of the projected quantities.  The small projected eigenproblem (subspace dimension
 // <= ncv) is diagonalised on the host with cyclic Jacobi.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -381,7 +383,12 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     bool done = false;
     double spmv_ms = 0.0;
     long iter = 0;
+    // PYCI_B200_SOLVER_TRACE: host wall time per phase (every phase ends in a stream synchronisation)
+    const bool trace = getenv("PYCI_B200_SOLVER_TRACE") != nullptr;
+    double tr[4] = {0, 0, 0, 0};
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (; iter < maxiter; ++iter) {
+        double tp = now();
         // images of the new basis vectors and the new rows/columns of G
         for (int j = m - nnew; j < m; ++j) {
             PYCI_TRY(S.apply(S.V + (size_t)j * S.ld, S.W + (size_t)j * S.ld));
@@ -392,12 +399,16 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             for (int i = 0; i < m; ++i)
                 G[(size_t)i * mmax + j] = G[(size_t)j * mmax + i] = col[i];
         }
+        tr[0] += now() - tp;
+        tp = now();
         // Rayleigh-Ritz
         Gw.assign((size_t)m * m, 0.0);
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j)
                 Gw[(size_t)i * m + j] = 0.5 * (G[(size_t)i * mmax + j] + G[(size_t)j * mmax + i]);
         jacobi_eigh(Gw, m, theta, Z);
+        tr[1] += now() - tp;
+        tp = now();
         // residuals and corrections
         const int nr = std::min(nroot, m);
         PYCI_CUDA(cudaMemsetAsync(S.dsmall + S.small_cap - nroot, 0, sizeof(double) * nroot, S.st));
@@ -428,6 +439,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
         }
         S.stats.residual = worst;
         S.stats.iterations = iter + 1;
+        tr[2] += now() - tp;
+        tp = now();
         if (all || m == nrow) {
             // m == nrow: the subspace is the whole space, the Ritz pairs are exact
             done = (nr == nroot);
@@ -473,7 +486,11 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             ++m;
             nnew = 1;
         }
+        tr[3] += now() - tp;
     }
+    if (trace)
+        fprintf(stderr, "[pyci_b200 solver] rank %d: %ld iterations, apply+dots %.3f s, jacobi %.3f s, ritz/residual %.3f s, "
+                        "orthogonalise/expand %.3f s\n", ctx->rank, (long)S.stats.iterations, tr[0], tr[1], tr[2], tr[3]);
     PYCI_CUDA(cudaEventRecord(t_end, S.st));
     PYCI_CUDA(cudaStreamSynchronize(S.st));
     float total_ms = 0;

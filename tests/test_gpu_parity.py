@@ -501,3 +501,33 @@ def test_hci_table_growth_and_c_abi(pyci):
     wfn.close()
     ham.close()
     ctx.close()
+
+
+def test_hci_enpt2_row_chunks_merge(pyci, monkeypatch):
+    """PYCI_B200_EXT_SPLIT walks the rows in chunks with one external table each and merges the chunk lists with the
+    kernel that also merges the per-rank lists of the row-sharded path: same result as the single walk."""
+    n, occ = 10, (3, 3)
+    ecore, one, two = O.synthetic_integrals(n, 4321)
+    ham = pyci.hamiltonian(ecore, one, two)
+    full = pyci.fullci_wfn(n, *occ)
+    full.add_all_dets()
+    fd = np.ascontiguousarray(full.to_det_array()[::9])
+    c = seeded_vec(len(fd), 3)
+    c /= np.linalg.norm(c)
+    pto, nt = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, -1.0, ecore, 0.02)
+    ref_new = O.add_hci(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, 0.02)
+    gd = np.ascontiguousarray((fd[:, 0] | (fd[:, 1] << np.uint64(n))).reshape(-1, 1))
+    h2, g2 = O.spin_orbital_integrals(one, two)
+    hamg = pyci.hamiltonian(ecore, h2, g2)
+    ref_newg = O.add_hci(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), c, 0.02)
+    for split in ("2", "3", "7"):
+        monkeypatch.setenv("PYCI_B200_EXT_SPLIT", split)
+        wfn = pyci.fullci_wfn(n, occ[0], occ[1], fd)
+        pt = pyci.compute_enpt2(ham, wfn, c, -1.0, 0.02)
+        assert abs(pt - pto) <= PT2_RTOL * abs(pto), (split, pt, pto)
+        assert pyci.add_hci(ham, wfn, c, eps=0.02) == len(ref_new)
+        assert np.array_equal(wfn.to_det_array()[len(fd):], ref_new)
+        wg = pyci.genci_wfn(2 * n, sum(occ), 0, gd)
+        assert abs(pyci.compute_enpt2(hamg, wg, c, -1.0, 0.02) - pto) <= PT2_RTOL * abs(pto)
+        assert pyci.add_hci(hamg, wg, c, eps=0.02) == len(ref_newg)
+        assert np.array_equal(wg.to_det_array()[len(gd):], ref_newg)
