@@ -161,7 +161,9 @@ def load_reference(genci=False):
     oracle/Makefile ("reference"); else None and the caller uses the oracle port.  GenCI uses
     pyci_ref_gencifix (two loop bounds of sparseop.cpp:453,476 corrected; the stock GenCI kernels are defective)."""
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    name = "pyci_ref_gencifix" if genci else "pyci_ref"
+    # one build per process: both register the same pybind11 types.  The GenCI-fixed build differs from the stock
+    # one only in the two GenCI loop bounds of sparseop.cpp, so it also serves every DOCI / FullCI call.
+    name = "pyci_ref_gencifix" if (genci or "pyci_ref_gencifix" in sys.modules) else "pyci_ref"
     if os.path.isdir(os.path.join(ref_dir, name)):
         sys.path.insert(0, ref_dir)
         try:
@@ -349,7 +351,9 @@ def run_b200(args, spec, rank, world, local):
         ctx.init_comm(rank, world, exchange_unique_id(cabi.nccl_unique_id, rank, world))
 
     # ---- host inputs (numpy arrays / host wave function), built once, untimed
+    note("building host inputs: " + spec["label"])
     ham, wfn = make_problem(pyci, spec)
+    note("host inputs ready: %d determinants" % len(wfn))
     ndet = len(wfn)
     kind = {"doci": cabi.DOCI, "fullci": cabi.FULLCI, "genci": cabi.GENCI}[spec["kind"]]
     dets = wfn.to_det_array()
@@ -369,6 +373,7 @@ def run_b200(args, spec, rank, world, local):
 
     for _ in range(args.warmup):
         step_device()
+    note("warm-up done, timing %d constructions" % args.steps)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -393,6 +398,7 @@ def run_b200(args, spec, rank, world, local):
     kernel_s = max_over_ranks(float(np.mean(per_step)))
 
     # ---- SpMV: per-launch CUDA events inside the library, on the same stream
+    note("SpMV timing")
     reps = max(args.steps, 10)
     ms = op.time_spmv(max(args.warmup, 3), reps, 0)
     spmv_ms = max_over_ranks(float(np.mean(ms)))
@@ -423,6 +429,7 @@ def run_b200(args, spec, rank, world, local):
         pass
 
     # ---- time to E0: one more construction + the Davidson solve, device-timed
+    note("time to E0")
     barrier()
     t0 = time.perf_counter()
     step_device()
@@ -437,6 +444,7 @@ def run_b200(args, spec, rank, world, local):
 
     # ---- 1- and 2-RDM of the ground state through the public API (collective when row-sharded), checked by
     # the energy identity of the reference's test_compute_rdms (test_routines.py:115-133)
+    note("RDMs")
     barrier()
     t0 = time.perf_counter()
     d1, d2 = pyci.compute_rdms(wfn, evecs[0])
@@ -444,6 +452,12 @@ def run_b200(args, spec, rank, world, local):
     rdm_wall = max_over_ranks(time.perf_counter() - t0)
     rdm_err = abs(rdm_energy(pyci, ham, spec, wfn, d1, d2) - float(evals[0])) if rank == 0 else 0.0
     del evecs, d1, d2
+
+    # ---- selected CI on a thinned FullCI space: one heat-bath iteration (add_hci) and the ENPT2 energy, device
+    # seconds of the walk + merge; the reference's own routines timed beside them on a row sample (rank 0)
+    barrier()
+    note("selected-CI leg")
+    sel = selected_ci_leg(cabi, ctx, rank, world, not args.no_cpu_baseline, spec["kind"] == "genci")
 
     # ---- end to end through the public API, host buffers in, row pointer out
     d2h_bytes = 0
@@ -455,6 +469,7 @@ def run_b200(args, spec, rank, world, local):
         d2h_bytes = ip.nbytes
         return o.size, int(ip[-1])
 
+    note("end-to-end leg")
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
     barrier()
@@ -500,9 +515,12 @@ def run_b200(args, spec, rank, world, local):
                        "spmv_seconds": st["spmv_seconds"]},
         "rdm": {"seconds_wall": rdm_wall, "energy_identity_abs_error": rdm_err,
                 "call": "pyci_b200.compute_rdms(wfn, c0): wfn upload + index + contraction + tensors back"},
+        "selected_ci": sel,
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        note("CPU baseline (reference, host cores)")
         line["cpu_baseline"] = cpu_sample(spec, args.cpu_seconds)
+    note("done")
     if rank == 0:
         emit(line)
     dwfn.close()
@@ -512,6 +530,53 @@ def run_b200(args, spec, rank, world, local):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+HCI_N, HCI_OCC, HCI_STRIDE, HCI_EPS = 16, (4, 4), 33, 2.0e-4
+
+
+def selected_ci_leg(cabi, ctx, rank, world, with_cpu, genci_ref):
+    """add_hci + compute_enpt2 on every 33rd determinant of FullCI(16, 4a4b) with a seeded
+    coefficient vector: device seconds (max over ranks is taken by the collective itself: every rank ends with the
+    merged result), and the compiled reference on the first rows of the same space, single-threaded like its build."""
+    syn = _synthetic()
+    _, one, two = syn.synthetic_integrals(HCI_N, SEED)
+    import pyci_b200 as pyci
+    full = pyci.fullci_wfn(HCI_N, *HCI_OCC)
+    full.add_all_dets()
+    dets = np.ascontiguousarray(full.to_det_array()[::HCI_STRIDE])
+    del full
+    c = np.random.default_rng(1).standard_normal(len(dets))
+    c /= np.linalg.norm(c)
+    ham = cabi.Ham(ctx, HCI_N, 0.0, one, two)
+    out = {"workload": "FullCI(%d, %da%db), every %dth determinant, eps %g" % (HCI_N, HCI_OCC[0], HCI_OCC[1], HCI_STRIDE, HCI_EPS),
+           "ndet": int(len(dets))}
+    for rep in range(2):  # second pass: warm allocations
+        wfn = cabi.Wfn(ctx, cabi.FULLCI, HCI_N, HCI_OCC[0], HCI_OCC[1], dets)
+        pt, nt = wfn.compute_enpt2(ham, c, -10.0, HCI_EPS)
+        out["enpt2_seconds_device"], out["external_determinants"], out["enpt2"] = wfn.ext_seconds(), int(nt), pt
+        new = wfn.add_hci(ham, c, HCI_EPS)
+        out["add_hci_seconds_device"], out["added"] = wfn.ext_seconds(), int(len(new))
+        wfn.close()
+    ham.close()
+    na, nv = HCI_OCC[0], HCI_N - HCI_OCC[0]
+    cand = 2 * na * nv + 2 * (na * (na - 1) // 2) * (nv * (nv - 1) // 2) + (na * nv) ** 2
+    out["rows_per_s"] = len(dets) / out["add_hci_seconds_device"]
+    out["candidates_per_s"] = cand * len(dets) / out["add_hci_seconds_device"]
+    if with_cpu and rank == 0 and world == 1:
+        ref, kind = load_reference(genci_ref)
+        if ref is not None:
+            k = 3000
+            rham = ref.secondquant_op(0.0, one, two)
+            rw = ref.fullci_wfn(HCI_N, HCI_OCC[0], HCI_OCC[1], dets[:k])
+            t0 = time.perf_counter()
+            ref.compute_enpt2(rham, rw, c[:k], -10.0, HCI_EPS, 1)
+            t1 = time.perf_counter()
+            ref.add_hci(rham, rw, c[:k], HCI_EPS, 1)
+            t2 = time.perf_counter()
+            out["cpu_reference"] = {"kind": kind, "cores": 1, "sample": "first %d determinants" % k,
+                                    "enpt2_rows_per_s": k / (t1 - t0), "add_hci_rows_per_s": k / (t2 - t1)}
+    return out
 
 
 def rdm_energy(pyci, ham, spec, wfn, d1, d2):
@@ -526,6 +591,15 @@ def rdm_energy(pyci, ham, spec, wfn, d1, d2):
 
 
 _JSON_OUT = None
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """progress line on stderr (rank 0), with seconds since start"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
 
 
 def claim_stdout():

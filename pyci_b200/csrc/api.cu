@@ -311,14 +311,8 @@ int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long noc
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
     PYCI_TRY(ctx_activate(ctx));
     const int nwords = (kind == PYCI_FULLCI) ? 2 : 1;
-    // every string must hold the declared number of electrons inside nbasis orbitals
-    const u64 valid = (nbasis == 64) ? ~0ULL : ((1ULL << nbasis) - 1ULL);
-    for (long i = 0; i < ndet; ++i) {
-        const u64 a = dets[i * nwords], b = (nwords == 2) ? dets[i * nwords + 1] : 0ULL;
-        if ((a & ~valid) || (b & ~valid) || __builtin_popcountll(a) != nocc_up ||
-            (nwords == 2 && __builtin_popcountll(b) != nocc_dn))
-            PYCI_FAIL(PYCI_ERR_VALUE, "determinant %ld does not have the declared occupation", i);
-    }
+    // that every string holds the declared number of electrons inside nbasis orbitals is checked on the device,
+    // together with uniqueness, by the verify pass of the index build
     pyci_wfn *wfn = new pyci_wfn();
     wfn->ctx = ctx;
     wfn->kind = kind;

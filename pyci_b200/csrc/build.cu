@@ -33,8 +33,12 @@ __global__ void diag_kernel(BuildParams P) {
 constexpr int UNROLL = 4;
 
 // ---- count pass ---------------------------------------------------------------------------------
+// hitlist != nullptr: the hits of a row (candidate index, column) are also recorded, up to `cap` per row, so that
+// the fill pass of a sparse (selected) space evaluates and sorts only those instead of enumerating and probing
+// every excitation a second time; rows with more hits than `cap` are enumerated again by the fill pass.
 template<int KIND, int KM>
-__global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb) {
+__global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb, uint2 *hitlist,
+                                                    int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RowTables T = carve_tables(smem_raw, nSa, nSb);
     uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw + tables_bytes(nSa, nSb));
@@ -42,15 +46,18 @@ __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> 
     __shared__ int warp_sums[8];
     fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
     for (long r = blockIdx.x; r < P.nloc; r += gridDim.x) {
         const long row = P.row0 + r;
         __syncthreads();
-        row_setup(rs, P, row, nspin);
+        row_setup(rs, P, row, nspin); // rs.count = 0: slot counter of the recorded hits
         __syncthreads();
         if (KIND != PYCI_DOCI) {
             build_tables<KIND, false>(P, rs, T, nSa, nSb);
             __syncthreads();
         }
+        uint2 *hrow = hitlist ? hitlist + (size_t)r * cap : nullptr;
         int cnt = 0;
         for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
             int hit[UNROLL];
@@ -66,8 +73,22 @@ __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> 
                 }
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-                cnt += (hit[u] >= 0 && hit[u] < P.ncol);
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
+                cnt += keep;
+                if (hrow) { // warp-aggregated append
+                    const u32 msk = __ballot_sync(0xffffffffu, keep);
+                    if (msk) {
+                        int slot = 0;
+                        const int leader = __ffs(msk) - 1;
+                        if (lane == leader)
+                            slot = atomicAdd(&rs.count, __popc(msk));
+                        slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(msk & lt);
+                        if (keep && slot < cap)
+                            hrow[slot] = make_uint2(base + u * blockDim.x + threadIdx.x, (u32)hit[u]);
+                    }
+                }
+            }
         }
         // block reduce
         for (int o = 16; o > 0; o >>= 1)
@@ -205,8 +226,10 @@ __device__ u64 *block_radix_sort(u64 *a, u64 *b, int m, int passes, int dbits, u
 
 // LAZY: evaluate the matrix element only for candidates that hit (selected spaces where most excitations
 // leave the wave function); otherwise element loads are issued together with the probes.
+// hitlist != nullptr: rows whose hits were recorded by the count pass (at most `cap`) are assembled from the record.
 template<int KIND, int KM, bool LAZY>
-__global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb) {
+__global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb,
+                                                   const uint2 *__restrict__ hitlist, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys A | keys B | values | radix counters | excitation tables | pair table
     u64 *keyA = reinterpret_cast<u64 *>(smem_raw);
@@ -241,42 +264,61 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         }
         __syncthreads();
         int nlow = 0;
-        for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
-            int hit[UNROLL];
-            double val[UNROLL];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const u32 c = base + u * blockDim.x + threadIdx.x;
-                hit[u] = -1;
-                val[u] = 0.0;
-                if (c < P.ncand) {
-                    u64 A, B;
-                    if (LAZY)
-                        candidate<KIND, false>(P, rs, T, pairs, c, A, B, val[u]);
-                    else
-                        candidate<KIND, true>(P, rs, T, pairs, c, A, B, val[u]);
-                    hit[u] = index.find(A, B);
-                }
+        const int ndiag = (row < P.ncol) ? 1 : 0; // the diagonal took slot 0 above
+        const int nh = (int)(P.indptr[r + 1] - P.indptr[r]) - ndiag;
+        if (hitlist != nullptr && nh <= cap) {
+            // sparse row recorded by the count pass: evaluate the hits only (no enumeration, no probes)
+            const uint2 *hrow = hitlist + (size_t)r * cap;
+            for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+                const uint2 h = hrow[k];
+                u64 A, B;
+                double v;
+                candidate<KIND, true>(P, rs, T, pairs, h.x, A, B, v);
+                const int slot = ndiag + k;
+                keyA[slot] = ((u64)h.y << 32) | (u32)slot;
+                valbuf[slot] = v;
+                nlow += ((long)h.y <= row);
             }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                // warp-aggregated append: one shared atomic per warp per step
-                const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
-                if (LAZY && keep) {
-                    u64 A, B;
-                    candidate<KIND, true>(P, rs, T, pairs, base + u * blockDim.x + threadIdx.x, A, B, val[u]);
+            if (threadIdx.x == 0)
+                rs.count = ndiag + nh;
+        } else {
+            for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
+                int hit[UNROLL];
+                double val[UNROLL];
+    #pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const u32 c = base + u * blockDim.x + threadIdx.x;
+                    hit[u] = -1;
+                    val[u] = 0.0;
+                    if (c < P.ncand) {
+                        u64 A, B;
+                        if (LAZY)
+                            candidate<KIND, false>(P, rs, T, pairs, c, A, B, val[u]);
+                        else
+                            candidate<KIND, true>(P, rs, T, pairs, c, A, B, val[u]);
+                        hit[u] = index.find(A, B);
+                    }
                 }
-                const u32 msk = __ballot_sync(0xffffffffu, keep);
-                if (msk) {
-                    int slot = 0;
-                    const int leader = __ffs(msk) - 1;
-                    if (lane == leader)
-                        slot = atomicAdd(&rs.count, __popc(msk));
-                    slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(msk & lt);
-                    if (keep) {
-                        keyA[slot] = ((u64)(u32)hit[u] << 32) | (u32)slot;
-                        valbuf[slot] = val[u];
-                        nlow += ((long)hit[u] <= row);
+    #pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    // warp-aggregated append: one shared atomic per warp per step
+                    const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
+                    if (LAZY && keep) {
+                        u64 A, B;
+                        candidate<KIND, true>(P, rs, T, pairs, base + u * blockDim.x + threadIdx.x, A, B, val[u]);
+                    }
+                    const u32 msk = __ballot_sync(0xffffffffu, keep);
+                    if (msk) {
+                        int slot = 0;
+                        const int leader = __ffs(msk) - 1;
+                        if (lane == leader)
+                            slot = atomicAdd(&rs.count, __popc(msk));
+                        slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(msk & lt);
+                        if (keep) {
+                            keyA[slot] = ((u64)(u32)hit[u] << 32) | (u32)slot;
+                            valbuf[slot] = val[u];
+                            nlow += ((long)hit[u] <= row);
+                        }
                     }
                 }
             }
@@ -447,12 +489,20 @@ __global__ void insert_kernel(typename SlotOf<KM>::type *slots, u32 mask, int sh
     }
 }
 
+// every determinant is re-found at its own position (duplicates are not) and holds the declared number of
+// electrons inside nbasis orbitals (Wfn::init / add_det preconditions); bad[0] = duplicates, bad[1] = first
+// determinant with a wrong occupation (INT_MAX if none)
 template<int KM>
-__global__ void verify_kernel(DetIndex<KM> ix, const u64 *dets, int nwords, long ndet, int *bad) {
+__global__ void verify_kernel(DetIndex<KM> ix, const u64 *dets, int nwords, long ndet, u64 valid, int nocc_up,
+                              int nocc_dn, int *bad) {
     const long idet = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idet >= ndet)
         return;
     const u64 a = dets[idet * nwords], b = (nwords == 2) ? dets[idet * nwords + 1] : 0ULL;
+    if ((a & ~valid) || (b & ~valid) || __popcll(a) != nocc_up || (nwords == 2 && __popcll(b) != nocc_dn)) {
+        atomicMin(bad + 1, (int)idet);
+        return;
+    }
     if (ix.find(a, b) != (int)idet)
         atomicAdd(bad, 1);
 }
@@ -490,16 +540,21 @@ int build_index_t(pyci_wfn *wfn) {
                                                              wfn->dets, wfn->nwords, ndet);
         ctx->launches++;
         int *bad = nullptr;
-        PYCI_CUDA(dev_malloc(&bad, sizeof(int)));
-        PYCI_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-        verify_kernel<KM><<<blocks, threads, 0, ctx->stream>>>(make_index<KM>(wfn), wfn->dets, wfn->nwords, ndet, bad);
+        const int init[2] = {0, 0x7fffffff};
+        PYCI_CUDA(dev_malloc(&bad, 2 * sizeof(int)));
+        PYCI_CUDA(cudaMemcpyAsync(bad, init, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        const u64 valid = (wfn->nbasis >= 64) ? ~0ULL : ((1ULL << wfn->nbasis) - 1ULL);
+        verify_kernel<KM><<<blocks, threads, 0, ctx->stream>>>(make_index<KM>(wfn), wfn->dets, wfn->nwords, ndet, valid,
+                                                               (int)wfn->nocc_up, (int)wfn->nocc_dn, bad);
         ctx->launches++;
-        int hbad = 0;
-        PYCI_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        int hbad[2] = {0, 0x7fffffff};
+        PYCI_CUDA(cudaMemcpyAsync(hbad, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
         dev_free(bad);
-        if (hbad)
-            PYCI_FAIL(PYCI_ERR_VALUE, "wave function contains %d duplicate determinant(s)", hbad);
+        if (hbad[1] != 0x7fffffff)
+            PYCI_FAIL(PYCI_ERR_VALUE, "determinant %d does not have the declared occupation", hbad[1]);
+        if (hbad[0])
+            PYCI_FAIL(PYCI_ERR_VALUE, "wave function contains %d duplicate determinant(s)", hbad[0]);
     }
     return PYCI_OK;
 }
@@ -624,6 +679,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     auto pick_block = [](long work) { return work <= 128 ? 32 : work <= 512 ? 64 : work <= 1024 ? 128 : 256; };
 
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], st));
+    uint2 *hitlist = nullptr; // (candidate, column) of the hits found by the count pass, [nloc][hitcap]
+    int hitcap = 0;
     int *rowcnt = nullptr;
     PYCI_CUDA(dev_malloc(&rowcnt, sizeof(int) * (size_t)(nloc + 1)));
     P.rowcnt = rowcnt;
@@ -642,7 +699,22 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             PYCI_CUDA(cudaFuncSetAttribute(count_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
             PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<KIND, KM>, block, csmem));
             const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb);
+            // sparse (selected) spaces on the general fill path: record the hits of the count pass
+            {
+                bool sorted_path = false;
+                if constexpr (KIND == PYCI_FULLCI)
+                    sorted_path = wfn->sorted2 && P.nAB > 0 && binom_d(P.n, P.nocc_a) <= 65536.0 &&
+                                  binom_d(P.n, P.nocc_b) <= 65536.0 && !getenv("PYCI_B200_NO_SORTED_PATH");
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                const long budget = (long)(free_b / 4);
+                long c = std::min<long>(1024, std::min<long>((long)P.ncand, budget / (8 * std::max<long>(nloc, 1))));
+                if (!sorted_path && P.ncand >= 2048 && c >= 32 && !getenv("PYCI_B200_NO_HITLIST")) {
+                    hitcap = (int)c;
+                    PYCI_CUDA(dev_malloc(&hitlist, sizeof(uint2) * (size_t)nloc * (size_t)hitcap));
+                }
+            }
+            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
             ctx->launches++;
         }
     }
@@ -767,18 +839,19 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, true>, block, smem));
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                fill_kernel<KIND, KM, true><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+                fill_kernel<KIND, KM, true><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
             } else {
                 PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, false>, block, smem));
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb);
+                fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
             }
             ctx->launches++;
             op->fill_kernel = "fill_kernel";
         }
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[3], st));
+    dev_free(hitlist);
     PYCI_CUDA(cudaStreamSynchronize(st));
     PYCI_CUDA(cudaGetLastError());
     float ms01 = 0, ms12 = 0;
