@@ -462,10 +462,17 @@ def run_b200(args, spec, rank, world, local):
     # ---- end to end through the public API, host buffers in, row pointer out
     d2h_bytes = 0
 
+    split = [0.0, 0.0]
+
     def step_e2e():
         nonlocal d2h_bytes
+        ta = time.perf_counter()
         o = pyci.sparse_op(ham, wfn)
+        tb = time.perf_counter()
         ip = o.indptr()
+        tc = time.perf_counter()
+        split[0] += tb - ta
+        split[1] += tc - tb
         d2h_bytes = ip.nbytes
         return o.size, int(ip[-1])
 
@@ -473,6 +480,7 @@ def run_b200(args, spec, rank, world, local):
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
     barrier()
+    split[0] = split[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         sz, _ = step_e2e()
@@ -491,6 +499,7 @@ def run_b200(args, spec, rank, world, local):
                          % (spmv_bytes / 1e9) if spmv_bytes > 4 * 126e6 else "operator fits L2: numbers are L2-resident"},
         "e2e": {"value": e2e_value, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "ms_sparse_op": 1e3 * split[0] / args.steps, "ms_indptr": 1e3 * split[1] / args.steps,
                 "call": "pyci_b200.sparse_op(ham, wfn); op.indptr()  (host arrays in, pageable)"},
         "gpu_launches": int(launches),
         "clocks": clocks,

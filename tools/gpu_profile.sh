@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_launches_run.log 2>&1
 echo "ncu list rc=$?"
 # full capture of the hot kernels on a smaller problem (ncu replays every launch ~40 times)
-ncu --set full --clock-control none --import-source on -k regex:'fill_complete_kernel|fill_sorted_kernel|fill_kernel|spmv_rows' -c 4 \
+ncu --set full --clock-control none --import-source on -k regex:'fill_complete_kernel|fill_sorted_kernel|fill_kernel|spmv_rows' -c 3 \
     -o $OUT/${TAG}_full -f python bench.py --workload $FULLW --steps 1 --warmup 0 --no-cpu-baseline > $OUT/${TAG}_full_run.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT
