@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = (u32)(P.n * P.n);
     const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
-    uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot | parity << 31, colex(A') * Nb, parity << 31 | n^3 i + n a
+    uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
     double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
     double *d_val = s_pre + nSa;
@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     const u32 w0 = (L1b <= 256u) ? t - gq * L1b : t;
     const bool ab_active = (L1b > 256u) || gq < GP;
     const u32 Uda = (nDa + 31) >> 5, Usa = (nSa + 31) >> 5;
+    // Work balance inside a group (all eight warps meet at the FULL barrier of every row, so the slowest warp sets
+    // the pace): the alpha-beta walk loads every warp alike; the short segments are dealt to different warps through
+    // rotated thread indices -- the second trip of the A' = A list to warps 3-4 (tA), the beta singles to warps 1-2
+    // (tB), the alpha-side units from warp 7 downwards (wq) -- and warp 0 keeps the bulk stores.
+    const u32 tA = (t + 160u) & 255u, tB = (t + 224u) & 255u;
     const u32 ra_first = (u32)((P.row0 + rbeg) / Nb), ra_last = (u32)((P.row0 + rend - 1) / Nb);
     for (u32 ra = ra_first; ra <= ra_last; ++ra) {
         // ---- stage the alpha string's tables
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             const size_t bS = (size_t)ra * nSa, bD = (size_t)ra * nDa;
             for (u32 g = threadIdx.x; g < nSa; g += blockDim.x) {
                 const u32 aux = C.A.s_aux[bS + g];
-                s_pack[g] = make_uint4(C.A.s_off[bS + g] | (aux & 0x80000000u), C.A.s_cr[bS + g] * Nb, aux, 0u);
+                s_pack[g] = make_uint4(C.A.s_off[bS + g], C.A.s_cr[bS + g] * Nb, aux & 0x7fffffffu, aux & 0x80000000u);
                 s_pre[g] = C.A.s_pre[bS + g];
             }
             for (u32 d = threadIdx.x; d < nDa; d += blockDim.x) {
@@ -313,16 +318,16 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             double dv[2] = {0.0, 0.0};
 #pragma unroll
             for (int q = 0; q < 2; ++q) // the first 512 entries of the beta list (the rest, if any, below)
-                if (t + 256u * q < Lb) {
-                    cb[q] = __ldg(crB + t + 256u * q);
-                    dv[q] = __ldg(dvalB + t + 256u * q);
+                if (tA + 256u * q < Lb) {
+                    cb[q] = __ldg(crB + tA + 256u * q);
+                    dv[q] = __ldg(dvalB + tA + 256u * q);
                 }
             u32 ps = 0u, sgn1 = 0u;
             double tq[4] = {0.0, 0.0, 0.0, 0.0}, diag_r = 0.0;
-            if (t < L1b) { // beta single t of the sub-list (:382-394): position, parity, its first own-spin terms
-                ps = __ldg(C.B.pos1 + rb * L1b + t);
-                sgn1 = __ldg(subB + t).y & 0x80000000u;
-                const double *tb = C.B.terms + (size_t)(rb * L1b + t) * nb;
+            if (tB < L1b) { // beta single tB of the sub-list (:382-394): position, parity, its first own-spin terms
+                ps = __ldg(C.B.pos1 + rb * L1b + tB);
+                sgn1 = __ldg(subB + tB).y & 0x80000000u;
+                const double *tb = C.B.terms + (size_t)(rb * L1b + tB) * nb;
 #pragma unroll
                 for (u32 q = 0; q < 4; ++q)
                     if (q < nb)
@@ -341,54 +346,36 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                 __syncwarp();
             }
             bar_free_sync(group);
-            // ---- alpha-beta doubles (sparseop.cpp:318-337)
-            if (ab_active) {
-                for (u32 w = w0; w < L1b; w += 256) {
-                    if (w != w0)
-                        eb = __ldg(subB + w); // colex rank | parity << 31, n i + a << 18, n^2 i + a
-                    if (w == j1s)
-                        continue; // B' = B: the alpha single below
-                    const u32 kl = SLICE ? ((eb.y >> 18) & 0xfffu) : (eb.y & 0x3ffffu);
-#pragma unroll 4
-                    for (u32 g = gq; g < nSa; g += GP) {
-                        // SLICE needs the first two words only (8-byte shared load instead of 16)
-                        const uint2 a = *reinterpret_cast<const uint2 *>(s_pack + g);
-                        const double v = SLICE ? slice[g * nn + kl] : __ldg(two_mo + ((s_pack[g].z & 0x7fffffffu) + kl));
-                        const u32 slot = (a.x & 0x7fffffffu) + w;
-                        bcol[slot] = (int)(a.y + eb.x);
-                        bval[slot] = flip_sign(v, (a.x ^ eb.y) & 0x80000000u);
-                    }
-                }
-            }
+            // (the prefetched beta-side values are consumed first so that their registers are free in the walk below)
             // ---- A' = A: columns of the whole beta list, values of its doubles (:397-416)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const u32 w = t + 256u * q;
+                const u32 w = tA + 256u * q;
                 if (w < Lb) {
                     bcol[self_off + w] = (int)(self_colbase + (cb[q] & 0x7fffffffu));
                     if (cb[q] >> 31)
                         bval[self_off + w] = dv[q];
                 }
             }
-            for (u32 w = t + 512u; w < Lb; w += 256) {
+            for (u32 w = tA + 512u; w < Lb; w += 256) {
                 const u32 c2 = __ldg(crB + w);
                 bcol[self_off + w] = (int)(self_colbase + (c2 & 0x7fffffffu));
                 if (c2 >> 31)
                     bval[self_off + w] = __ldg(dvalB + w);
             }
             // ---- values of the beta singles (:382-394) and of the diagonal (:421-424)
-            for (u32 j1 = t; j1 < L1b; j1 += 256) {
-                if (j1 != t) {
+            for (u32 j1 = tB; j1 < L1b; j1 += 256) {
+                if (j1 != tB) {
                     ps = __ldg(C.B.pos1 + rb * L1b + j1);
                     sgn1 = __ldg(subB + j1).y & 0x80000000u;
                 }
                 const u32 slot = self_off + (ps & 0xffffu);
                 if (j1 == j1s) {
-                    bval[slot] = (j1 == t) ? diag_r : P.diag[r];
+                    bval[slot] = (j1 == tB) ? diag_r : P.diag[r];
                 } else {
                     const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
                     double v = JA[ps >> 16];
-                    if (j1 == t) {
+                    if (j1 == tB) {
 #pragma unroll
                         for (u32 q = 0; q < 4; ++q)
                             if (q < nb)
@@ -400,6 +387,30 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                             v += __ldg(tb + q);
                     }
                     bval[slot] = flip_sign(v, sgn1);
+                }
+            }
+            // ---- alpha-beta doubles (sparseop.cpp:318-337): per element two shared loads (alpha entry, integral),
+            // one add (column), one xor (sign) and two shared stores through pointers that already hold the beta
+            // entry's position w -- everything that depends on w alone is hoisted out of the walk over g
+            if (ab_active) {
+                for (u32 w = w0; w < L1b; w += 256) {
+                    if (w != w0)
+                        eb = __ldg(subB + w); // colex rank | parity << 31, n i + a << 18, n^2 i + a
+                    if (w == j1s)
+                        continue; // B' = B: the alpha single below
+                    const u32 kl = SLICE ? ((eb.y >> 18) & 0xfffu) : (eb.y & 0x3ffffu);
+                    const u32 sgn_b = eb.y & 0x80000000u, cr_b = eb.x;
+                    int *pc = bcol + w;
+                    double *pv = bval + w;
+                    const uint4 *pa = s_pack + gq;
+                    const double *psl = slice + gq * nn + kl;
+#pragma unroll 4
+                    for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += GP * nn) {
+                        const uint4 a = *pa;
+                        const double v = SLICE ? *psl : __ldg(two_mo + (a.z + kl));
+                        pc[a.x] = (int)(a.y + cr_b);
+                        pv[a.x] = flip_sign(v, a.w ^ sgn_b);
+                    }
                 }
             }
             // The alpha-side segments in units of 32 entries, dealt round-robin to the warps from the last one
@@ -423,12 +434,11 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     double v = s_pre[g];
                     for (u64 q = Bdet; q; q &= q - 1) {
                         const u32 kk = (u32)__ffsll((long long)q) - 1u;
-                        v += SLICE ? slice[g * nn + kk * (u32)n1 + kk]
-                                   : __ldg(two_mo + (a.z & 0x7fffffffu) + (u32)n2 * kk + kk);
+                        v += SLICE ? slice[g * nn + kk * (u32)n1 + kk] : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
                     }
-                    const u32 slot = (a.x & 0x7fffffffu) + j1s;
+                    const u32 slot = a.x + j1s;
                     bcol[slot] = (int)(a.y + rb);
-                    bval[slot] = flip_sign(v, a.x & 0x80000000u);
+                    bval[slot] = flip_sign(v, a.w);
                 }
             }
             // ---- the finished row goes out as two bulk copies (TMA): 16-byte aligned bodies of the value and
