@@ -643,6 +643,10 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.M = S.M;
     C.Nb = Nb;
     C.dSb = P.dSb;
+    C.nn = (u32)(P.n * P.n);
+    C.GP = std::max(1u, 256u / L1b);
+    C.GPnn = C.GP * C.nn;
+    C.dL1b = make_fastdiv(L1b);
     PYCI_CUDA(cudaFuncSetAttribute(string_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     string_table_kernel<<<std::min<u32>(Na, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.A, 0, (long)Nb, S.Wa, S.K1, S.binom,
                                                                                S.Lb, L1b);

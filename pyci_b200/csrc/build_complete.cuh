@@ -48,6 +48,9 @@ struct CompleteParams {
     u32 M;  // entries per row = ncand + 1
     u32 Nb; // C(n, nocc_b)
     FastDiv dSb;
+    // launch-time constants of the fill kernel (kept out of registers: the compiler re-derives them per use)
+    u32 nn, GP, GPnn; // n^2; walkers side by side in the alpha-beta segment = max(1, 256 / L1b); GP * n^2
+    FastDiv dL1b;     // division of the thread index by L1b
 };
 
 inline size_t string_table_smem(u32 W, u32 L, u32 n, u32 K1, size_t pair_bytes) {
@@ -236,7 +239,7 @@ template<bool SLICE>
 __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
-    const u32 nn = (u32)(P.n * P.n);
+    const u32 nn = C.nn;
     const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
     uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
@@ -257,8 +260,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
         return;
     // alpha-beta doubles: a thread keeps ONE entry of the beta sub-list (L1b <= 256) and walks the alpha singles
     // g = gq, gq + GP, ...; 256 / L1b such walkers side by side
-    const u32 GP = max(1u, 256u / L1b);
-    const u32 gq = (L1b <= 256u) ? t / L1b : 0u;
+    const u32 GP = C.GP;
+    const u32 gq = (L1b <= 256u) ? fdiv(t, C.dL1b) : 0u;
     const u32 w0 = (L1b <= 256u) ? t - gq * L1b : t;
     const bool ab_active = (L1b > 256u) || gq < GP;
     const u32 Uda = (nDa + 31) >> 5, Usa = (nSa + 31) >> 5;
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     const uint4 *pa = s_pack + gq;
                     const double *psl = slice + gq * nn + kl;
 #pragma unroll 4
-                    for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += GP * nn) {
+                    for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += C.GPnn) {
                         const uint4 a = *pa;
                         const double v = SLICE ? *psl : __ldg(two_mo + (a.z + kl));
                         pc[a.x] = (int)(a.y + cr_b);
