@@ -194,8 +194,12 @@ struct Solver {
     double *V = nullptr, *W = nullptr, *X = nullptr, *AX = nullptr, *T = nullptr;
     double *xfull = nullptr; // all-gather target (R > 1)
     double *dsmall = nullptr; // device scratch for dots / coefficients
-    double *hsmall = nullptr; // pinned host mirror
+    double *hsmall = nullptr; // pinned host mirror (results of dots)
+    double *hring = nullptr, *dring = nullptr; // coefficient staging ring: RING slots of small_cap doubles, host pinned
+                                               // + device, so that uploads need no synchronisation before reuse
+    int ring_pos = 0, ring_pending = 0; // uploads since the last stream synchronisation
     int small_cap = 0;
+    static constexpr int RING = 32;
     pyci_solve_stats stats;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 
@@ -209,6 +213,9 @@ struct Solver {
         dev_free(dsmall);
         if (hsmall)
             cudaFreeHost(hsmall);
+        if (hring)
+            cudaFreeHost(hring);
+        dev_free(dring);
         if (e0)
             cudaEventDestroy(e0);
         if (e1)
@@ -243,44 +250,104 @@ struct Solver {
                 PYCI_TRY(comm_allreduce_sum_f64(ctx, dsmall, kk));
             PYCI_CUDA(cudaMemcpyAsync(hsmall, dsmall, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
             PYCI_CUDA(cudaStreamSynchronize(st));
+            ring_pending = 0;
             std::memcpy(host + j0, hsmall, sizeof(double) * kk);
         }
         return PYCI_OK;
     }
 
-    // x = beta x + alpha * sum_j s_j Vb_j
-    int combine(const double *Vb, int k, const double *s_host, double alpha, double beta, double *x) {
-        if (k > small_cap)
+    // host[0..k) = Vb_j . w, host[k] = extra . w: one reduction, one synchronisation
+    int dots2(const double *Vb, int k, const double *extra, const double *w, double *host) {
+        if (k + 1 > small_cap)
             PYCI_FAIL(PYCI_ERR_RUNTIME, "subspace larger than scratch");
-        std::memcpy(hsmall, s_host, sizeof(double) * k);
-        PYCI_CUDA(cudaMemcpyAsync(dsmall, hsmall, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        combine_kernel<<<grid, RB, sizeof(double) * k, st>>>(Vb, ld, k, dsmall, alpha, beta, x, nloc);
+        PYCI_CUDA(cudaMemsetAsync(dsmall, 0, sizeof(double) * (k + 1), st));
+        for (int c0 = 0; c0 < k; c0 += KCHUNK) {
+            const int kc = std::min(KCHUNK, k - c0);
+            multi_dot_kernel<<<grid, RB, 0, st>>>(Vb + (long)c0 * ld, ld, kc, w, nloc, dsmall + c0);
+            ctx->launches++;
+        }
+        multi_dot_kernel<<<grid, RB, 0, st>>>(extra, ld, 1, w, nloc, dsmall + k);
         ctx->launches++;
-        PYCI_CUDA(cudaStreamSynchronize(st)); // hsmall is reused
+        if (R > 1)
+            PYCI_TRY(comm_allreduce_sum_f64(ctx, dsmall, k + 1));
+        PYCI_CUDA(cudaMemcpyAsync(hsmall, dsmall, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        ring_pending = 0;
+        std::memcpy(host, hsmall, sizeof(double) * (k + 1));
         return PYCI_OK;
     }
 
-    // orthogonalise t against V[0..m) (classical Gram-Schmidt, twice) and normalise; returns the norm
-    // of the orthogonal component relative to the input norm in *rel
+    // coefficients to the device through the staging ring; a slot is reused after RING uploads, and every Davidson
+    // iteration synchronises the stream at least twice, so a slot is never overwritten while its copy is pending
+    const double *stage(const double *s_host, int k, int *err) {
+        *err = PYCI_OK;
+        if (++ring_pending >= RING) { // many roots: do not lap a slot whose copy may still be pending
+            cudaStreamSynchronize(st);
+            ring_pending = 0;
+        }
+        double *h = hring + (size_t)ring_pos * small_cap, *d = dring + (size_t)ring_pos * small_cap;
+        ring_pos = (ring_pos + 1) % RING;
+        std::memcpy(h, s_host, sizeof(double) * k);
+        if (cudaMemcpyAsync(d, h, sizeof(double) * k, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            pyci_set_error("CUDA error while staging coefficients");
+            *err = PYCI_ERR_CUDA;
+        }
+        return d;
+    }
+
+    // x = beta x + alpha * sum_j s_j Vb_j   (asynchronous)
+    int combine(const double *Vb, int k, const double *s_host, double alpha, double beta, double *x) {
+        if (k > small_cap)
+            PYCI_FAIL(PYCI_ERR_RUNTIME, "subspace larger than scratch");
+        int err;
+        const double *d = stage(s_host, k, &err);
+        PYCI_TRY(err);
+        combine_kernel<<<grid, RB, sizeof(double) * k, st>>>(Vb, ld, k, d, alpha, beta, x, nloc);
+        ctx->launches++;
+        return PYCI_OK;
+    }
+
+    // Orthogonalise t against V[0..m) (classical Gram-Schmidt, twice) and normalise.  Each pass takes ONE batch
+    // of dot products, [V_0..V_{m-1}, t] . t, i.e. one reduction and one synchronisation; V is orthonormal, so
+    // the norm after the second pass is |t|^2 - sum_j (V_j . t)^2 and the scaling rides on the second update.
+    // *rel = norm of the orthogonal component relative to the input norm.
     int orthonormalize(double *t, int m, std::vector<double> &tmp, double *rel) {
-        double n0 = 0.0;
-        PYCI_TRY(dots(t, 1, t, &n0));
-        if (!(n0 > 0.0)) {
-            *rel = 0.0;
-            return PYCI_OK;
+        tmp.resize((size_t)m + 1);
+        double n0 = 0.0, n1 = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            // t sits at V + m * ld when it is the next basis vector; in general it is a separate buffer: two batches
+            if (m > 0)
+                PYCI_TRY(dots2(V, m, t, t, tmp.data()));
+            else
+                PYCI_TRY(dots(t, 1, t, tmp.data()));
+            const double tt = tmp[(size_t)m];
+            if (pass == 0) {
+                n0 = tt;
+                if (!(n0 > 0.0)) {
+                    *rel = 0.0;
+                    return PYCI_OK;
+                }
+                if (m > 0)
+                    PYCI_TRY(combine(V, m, tmp.data(), -1.0, 1.0, t));
+            } else {
+                double proj = 0.0;
+                for (int j = 0; j < m; ++j)
+                    proj += tmp[(size_t)j] * tmp[(size_t)j];
+                n1 = tt - proj;
+                if (!(n1 > 0.0)) {
+                    *rel = 0.0;
+                    return PYCI_OK;
+                }
+                const double inv = 1.0 / std::sqrt(n1);
+                if (m > 0) {
+                    PYCI_TRY(combine(V, m, tmp.data(), -inv, inv, t));
+                } else {
+                    scale_kernel<<<grid, RB, 0, st>>>(t, inv, nloc);
+                    ctx->launches++;
+                }
+            }
         }
-        for (int pass = 0; pass < 2 && m > 0; ++pass) {
-            tmp.resize(m);
-            PYCI_TRY(dots(V, m, t, tmp.data()));
-            PYCI_TRY(combine(V, m, tmp.data(), -1.0, 1.0, t));
-        }
-        double n1 = 0.0;
-        PYCI_TRY(dots(t, 1, t, &n1));
         *rel = std::sqrt(n1 / n0);
-        if (n1 > 0.0) {
-            scale_kernel<<<grid, RB, 0, st>>>(t, 1.0 / std::sqrt(n1), nloc);
-            ctx->launches++;
-        }
         return PYCI_OK;
     }
 };
@@ -327,6 +394,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     PYCI_CUDA(dev_malloc(&S.xfull, vec * R));
     PYCI_CUDA(dev_malloc(&S.dsmall, sizeof(double) * S.small_cap));
     PYCI_CUDA(cudaMallocHost(&S.hsmall, sizeof(double) * S.small_cap));
+    PYCI_CUDA(cudaMallocHost(&S.hring, sizeof(double) * S.small_cap * Solver::RING));
+    PYCI_CUDA(dev_malloc(&S.dring, sizeof(double) * S.small_cap * Solver::RING));
     PYCI_CUDA(cudaEventCreate(&S.e0));
     PYCI_CUDA(cudaEventCreate(&S.e1));
     cudaEvent_t t_begin, t_end;
@@ -416,13 +485,13 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
         for (int r = 0; r < nr; ++r) {
             for (int i = 0; i < m; ++i)
                 sj[i] = Z[(size_t)i * m + r];
-            std::memcpy(S.hsmall, sj.data(), sizeof(double) * m);
-            PYCI_CUDA(cudaMemcpyAsync(S.dsmall, S.hsmall, sizeof(double) * m, cudaMemcpyHostToDevice, S.st));
+            int err;
+            const double *dsj = S.stage(sj.data(), m, &err);
+            PYCI_TRY(err);
             ritz_residual_kernel<<<S.grid, RB, sizeof(double) * m, S.st>>>(
-                S.V, S.W, S.ld, m, S.dsmall, theta[r], op->diag, S.X + (size_t)r * S.ld, S.AX + (size_t)r * S.ld,
+                S.V, S.W, S.ld, m, dsj, theta[r], op->diag, S.X + (size_t)r * S.ld, S.AX + (size_t)r * S.ld,
                 S.T + (size_t)r * S.ld, S.nloc, S.dsmall + S.small_cap - nroot + r);
             ctx->launches++;
-            PYCI_CUDA(cudaStreamSynchronize(S.st));
         }
         if (R > 1)
             PYCI_TRY(comm_allreduce_sum_f64(ctx, S.dsmall + S.small_cap - nroot, nroot));
