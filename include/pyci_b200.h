@@ -129,6 +129,13 @@ PYCI_API double pyci_wfn_ext_seconds(const pyci_wfn *wfn);
 PYCI_API int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
                   int symmetric, pyci_op **out);
 PYCI_API void pyci_op_destroy(pyci_op *op);
+/* SparseOp::update (sparseop.cpp:175-201): grow a square symmetric operator built for the first op.nrow
+ * determinants of wfn to all wfn.ndet of them (the caller appended determinants, e.g. with pyci_wfn_add_hci; the
+ * first op.nrow determinants must be the ones the operator was built from, as for the reference).  Only the new
+ * determinants are enumerated: their rows are built, and their entries with an old column are transposed into
+ * the ends of the old rows (the device keeps full rows).  The exported CSR equals that of a fresh build.
+ * PYCI_ERR_UNSUPPORTED for non-symmetric / rectangular operators and when row-sharded: rebuild instead. */
+PYCI_API int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn);
 
 PYCI_API long pyci_op_nrow(const pyci_op *op);
 PYCI_API long pyci_op_ncol(const pyci_op *op);

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "pyci_wfn_ext_seconds": (_d, [_vp]),
     "pyci_op_build": (_i, [_vp, _vp, _vp, _l, _l, _i, _vpp]),
     "pyci_op_destroy": (None, [_vp]),
+    "pyci_op_update": (_i, [_vp, _vp, _vp]),
     "pyci_op_nrow": (_l, [_vp]),
     "pyci_op_ncol": (_l, [_vp]),
     "pyci_op_row_begin": (_l, [_vp]),
@@ -221,10 +222,18 @@ class Op:
         self.handle = ctypes.c_void_p()
         check(lib().pyci_op_build(ctx.handle, ham.handle, wfn.handle, nrow, ncol, int(bool(symmetric)),
                                   ctypes.byref(self.handle)))
+        self._refresh()
+
+    def _refresh(self):
         L = lib()
         self.nrow, self.ncol = L.pyci_op_nrow(self.handle), L.pyci_op_ncol(self.handle)
         self.row_begin, self.row_count = L.pyci_op_row_begin(self.handle), L.pyci_op_row_count(self.handle)
         self.size, self.stored_nnz = L.pyci_op_size(self.handle), L.pyci_op_stored_nnz(self.handle)
+
+    def update(self, ham, wfn):
+        """SparseOp::update: grow to all determinants now in wfn (incremental; square symmetric, one rank)."""
+        check(lib().pyci_op_update(self.handle, ham.handle, wfn.handle))
+        self._refresh()
 
     def close(self):
         if self.handle:

@@ -488,6 +488,23 @@ int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long 
     return PYCI_OK;
 }
 
+int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn) {
+    if (!op || !ham || !wfn)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    if (ham->nbasis != wfn->nbasis)
+        PYCI_FAIL(PYCI_ERR_VALUE, "ham.nbasis (%ld) != wfn.nbasis (%ld)", ham->nbasis, wfn->nbasis);
+    if (wfn->ndet < op->nrow)
+        PYCI_FAIL(PYCI_ERR_VALUE, "the wave function holds fewer determinants (%ld) than the operator has rows (%ld)",
+                  wfn->ndet, op->nrow);
+    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "incremental update needs a square symmetric operator on one rank: rebuild instead");
+    if (wfn->kind == PYCI_DOCI ? (!ham->h || !ham->v || !ham->w) : (!ham->one_mo || !ham->two_mo))
+        PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian lacks the integrals this wave-function kind needs");
+    PYCI_TRY(ctx_activate(ctx));
+    return op_update_impl(ctx, ham, wfn, op);
+}
+
 void pyci_op_destroy(pyci_op *op) {
     if (!op)
         return;

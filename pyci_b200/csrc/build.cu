@@ -895,6 +895,30 @@ __global__ void lowcnt_sum_kernel(const int *lowcnt, long n, unsigned long long 
 
 } // namespace
 
+// indptr[0..n] = exclusive int64 scan of cnt[0..n) (indptr[n] = total); *maxcnt (device, may be null) = max cnt
+int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt) {
+    cudaStream_t st = ctx->stream;
+    const long nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    long *blocksum = nullptr;
+    int *mc = maxcnt;
+    PYCI_CUDA(dev_malloc(&blocksum, sizeof(long) * (size_t)(nb + 2)));
+    if (!mc)
+        PYCI_CUDA(dev_malloc(&mc, sizeof(int)));
+    PYCI_CUDA(cudaMemsetAsync(mc, 0, sizeof(int), st));
+    PYCI_CUDA(cudaMemsetAsync(indptr, 0, sizeof(long) * (size_t)(n + 1), st));
+    if (n > 0) {
+        scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, n, blocksum);
+        scan_of_sums<<<1, SCAN_BLOCK, 0, st>>>(blocksum, nb);
+        scan_finish<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(cnt, n, blocksum, indptr, mc);
+        ctx->launches += 3;
+    }
+    PYCI_CUDA(cudaGetLastError());
+    dev_free(blocksum);
+    if (!maxcnt)
+        dev_free(mc);
+    return PYCI_OK;
+}
+
 int wfn_build_index(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
     // capacity: power of two with load factor in (0.25, 0.5]

@@ -137,6 +137,9 @@ int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
 // build.cu
 int wfn_build_index(pyci_wfn *wfn);
 int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
+int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt);
+// update.cu
+int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
 // spmv.cu
 int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev);
 // solver.cu

@@ -99,10 +99,31 @@ void SparseOp::build(const SQuantOp &ham, const Wfn &wfn, long rows, long cols) 
     shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
 }
 
-// SparseOp::py_update (sparseop.cpp:175-178): extend to all determinants now in wfn.  The reference
-// appends rows [old nrow, ndet) to its lower-triangular storage; the device keeps full rows, so the
-// operator is rebuilt -- the exported CSR is identical.
-void SparseOp::update(const SQuantOp &ham, const Wfn &wfn) { build(ham, wfn, wfn.ndet, wfn.ndet); }
+// SparseOp::py_update (sparseop.cpp:175-178): extend to all determinants now in wfn.  The reference appends rows
+// [old nrow, ndet) to its lower-triangular storage.  The device keeps full rows: pyci_op_update builds the new rows
+// and transposes their old-column entries into the old rows (only the new determinants are enumerated); operators
+// it does not cover (non-symmetric, rectangular, row-sharded) are rebuilt -- the exported CSR is identical.
+void SparseOp::update(const SQuantOp &ham, const Wfn &wfn) {
+    if (handle && symmetric && nrow == ncol && wfn.ndet >= nrow && pyci_ctx_nranks(device_context()) == 1) {
+        DeviceHam dham(ham);
+        DeviceWfn dwfn(wfn);
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            rc = pyci_op_update(handle, dham.h, dwfn.w);
+        }
+        if (rc == PYCI_OK) {
+            nrow = ncol = wfn.ndet;
+            ecore = ham.ecore;
+            size = pyci_op_size(handle);
+            shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
+            return;
+        }
+        if (rc != PYCI_ERR_UNSUPPORTED)
+            check(rc);
+    }
+    build(ham, wfn, wfn.ndet, wfn.ndet);
+}
 
 double SparseOp::get_element(long i, long j) const {
     if (i < 0 || i >= nrow || j < 0 || j >= ncol)
