@@ -541,7 +541,7 @@ def run_b200(args, spec, rank, world, local):
     return 0
 
 
-HCI_N, HCI_OCC, HCI_STRIDE, HCI_EPS = 16, (4, 4), 33, 2.0e-4
+HCI_N, HCI_OCC, HCI_STRIDE, HCI_EPS, HCI_EPS_UPDATE = 16, (4, 4), 33, 2.0e-4, 2.0e-2
 
 
 def selected_ci_leg(cabi, ctx, rank, world, with_cpu, genci_ref):
@@ -566,6 +566,29 @@ def selected_ci_leg(cabi, ctx, rank, world, with_cpu, genci_ref):
         out["enpt2_seconds_device"], out["external_determinants"], out["enpt2"] = wfn.ext_seconds(), int(nt), pt
         new = wfn.add_hci(ham, c, HCI_EPS)
         out["add_hci_seconds_device"], out["added"] = wfn.ext_seconds(), int(len(new))
+        wfn.close()
+    if world == 1:  # the incremental path is single-rank (row blocks move when the operator grows)
+        # SparseOp::update after a selection step that adds ~50 % more determinants: incremental growth (only the new
+        # determinants are enumerated) against a fresh construction of the grown operator
+        wfn = cabi.Wfn(ctx, cabi.FULLCI, HCI_N, HCI_OCC[0], HCI_OCC[1], dets)
+        op = cabi.Op(ctx, ham, wfn)
+        grown = wfn.add_hci(ham, c, HCI_EPS_UPDATE)
+        for rep in range(2):
+            if rep:  # second pass on a fresh copy of the small operator: warm allocations
+                op.close()
+                small = cabi.Wfn(ctx, cabi.FULLCI, HCI_N, HCI_OCC[0], HCI_OCC[1], dets)
+                op = cabi.Op(ctx, ham, small)
+                small.close()
+            op.update(ham, wfn)
+            upd = op.build_times()["total"]
+            fresh = cabi.Op(ctx, ham, wfn)
+            full = fresh.build_times()["total"]
+            same = (op.size == fresh.size) and (op.stored_nnz == fresh.stored_nnz)
+            fresh.close()
+        out["update"] = {"eps": HCI_EPS_UPDATE, "ndet_before": int(len(dets)), "ndet_after": int(wfn.ndet),
+                         "added": int(len(grown)), "stored_nnz_after": int(op.stored_nnz),
+                         "update_seconds_device": upd, "fresh_build_seconds_device": full, "same_size_as_fresh_build": bool(same)}
+        op.close()
         wfn.close()
     ham.close()
     na, nv = HCI_OCC[0], HCI_N - HCI_OCC[0]
