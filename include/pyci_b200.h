@@ -204,6 +204,16 @@ PYCI_API int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long
 PYCI_API int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1,
                       double *rdm2);
 
+/* compute_transition_rdms (rdm.cpp:634-1009): <Psi1| ... |Psi2> with the shapes of pyci_compute_rdms; rows run over
+ * wfn1, excited determinants are looked up in wfn2, every connected ordered pair contributes in one direction
+ * (T(wfn, wfn, c, c) = compute_rdms(wfn, c)).  Both wave functions must share kind, nbasis and occupations.
+ * GenCI: intended semantics (the reference routine is defective).  Collective when row-sharded. */
+PYCI_API int pyci_compute_transition_rdms(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2,
+                                 const double *coeffs1, const double *coeffs2, double *rdm1, double *rdm2);
+/* compute_overlap (overlap.cpp:17-58): sum over the determinants common to both wave functions of c1_i c2_j */
+PYCI_API int pyci_compute_overlap(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2, const double *coeffs1,
+                         const double *coeffs2, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,11 @@ def lib():
         L.oracle_enpt2.restype = ctypes.c_int
         L.oracle_enpt2.argtypes = [ctypes.c_int] + [ctypes.c_long] * 4 + [ctypes.c_void_p] * 4 + \
             [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_long)]
+        L.oracle_trdms_doci.argtypes = [ctypes.c_long] * 3 + [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_void_p] * 5
+        L.oracle_trdms_fullci.argtypes = [ctypes.c_long] * 4 + [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_void_p] * 5
+        L.oracle_trdms_genci.argtypes = [ctypes.c_long] * 3 + [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_void_p] * 5
+        L.oracle_overlap.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_void_p, ctypes.c_long] + \
+            [ctypes.c_void_p] * 3 + [ctypes.POINTER(ctypes.c_double)]
         L.oracle_binomial.restype = ctypes.c_long
         L.oracle_binomial.argtypes = [ctypes.c_long, ctypes.c_long]
         _LIB = L
@@ -259,6 +264,43 @@ def compute_enpt2(kind, nbasis, nocc_up, nocc_dn, dets, ints, coeffs, energy, ec
     if rc != 0:
         raise MemoryError("oracle_enpt2 failed")
     return out.value, nt.value
+
+
+def compute_transition_rdms(kind, nbasis, nocc_up, nocc_dn, dets1, dets2, coeffs1, coeffs2):
+    """Restates pyci.compute_transition_rdms(wfn1, wfn2, coeffs1, coeffs2) (rdm.cpp:634-1009; GenCI: intended
+    semantics, see pyci_oracle.c)."""
+    L = lib()
+    d1 = np.ascontiguousarray(dets1, dtype=np.uint64)
+    d2 = np.ascontiguousarray(dets2, dtype=np.uint64)
+    c1 = np.ascontiguousarray(coeffs1, dtype=np.float64)
+    c2 = np.ascontiguousarray(coeffs2, dtype=np.float64)
+    n = nbasis
+    if kind == DOCI:
+        r1, r2 = np.zeros((n, n)), np.zeros((n, n))
+        rc = L.oracle_trdms_doci(n, nocc_up, d1.shape[0], _p(d1), d2.shape[0], _p(d2), _p(c1), _p(c2), _p(r1), _p(r2))
+    elif kind == FULLCI:
+        r1, r2 = np.zeros((2, n, n)), np.zeros((3, n, n, n, n))
+        rc = L.oracle_trdms_fullci(n, nocc_up, nocc_dn, d1.shape[0], _p(d1), d2.shape[0], _p(d2), _p(c1), _p(c2),
+                                   _p(r1), _p(r2))
+    else:
+        r1, r2 = np.zeros((n, n)), np.zeros((n, n, n, n))
+        rc = L.oracle_trdms_genci(n, nocc_up, d1.shape[0], _p(d1), d2.shape[0], _p(d2), _p(c1), _p(c2), _p(r1), _p(r2))
+    if rc != 0:
+        raise MemoryError("oracle transition rdms failed")
+    return r1, r2
+
+
+def compute_overlap(dets1, dets2, coeffs1, coeffs2):
+    """Restates pyci.compute_overlap(wfn1, wfn2, coeffs1, coeffs2) (overlap.cpp:17-58)."""
+    d1 = np.ascontiguousarray(dets1, dtype=np.uint64)
+    d2 = np.ascontiguousarray(dets2, dtype=np.uint64)
+    nw = int(np.prod(d1.shape[1:]))
+    c1 = np.ascontiguousarray(coeffs1, dtype=np.float64)
+    c2 = np.ascontiguousarray(coeffs2, dtype=np.float64)
+    out = ctypes.c_double(0.0)
+    if lib().oracle_overlap(nw, d1.shape[0], _p(d1), d2.shape[0], _p(d2), _p(c1), _p(c2), ctypes.byref(out)) != 0:
+        raise MemoryError("oracle overlap failed")
+    return out.value
 
 
 def full_symmetric(indptr, indices, data, n):

@@ -29,7 +29,7 @@ from pyci_b200._pyci import __version__, c_long, c_ulong, c_double
 from pyci_b200._pyci import secondquant_op, wavefunction, one_spin_wfn, two_spin_wfn
 from pyci_b200._pyci import doci_wfn, fullci_wfn, genci_wfn, sparse_op
 from pyci_b200._pyci import get_num_threads, set_num_threads, popcnt, ctz
-from pyci_b200._pyci import compute_rdms, add_hci, compute_enpt2
+from pyci_b200._pyci import compute_rdms, add_hci, compute_enpt2, compute_transition_rdms, compute_overlap
 from pyci_b200._pyci import device_count, set_device, nccl_unique_id, init_comm
 from pyci_b200._pyci import launch_count, reset_launch_count, synchronize
 
@@ -43,7 +43,7 @@ __all__ = [
     "__version__", "c_long", "c_ulong", "c_double",
     "secondquant_op", "hamiltonian", "wavefunction", "one_spin_wfn", "two_spin_wfn",
     "doci_wfn", "fullci_wfn", "genci_wfn", "sparse_op",
-    "get_num_threads", "set_num_threads", "popcnt", "ctz", "compute_rdms", "add_hci", "compute_enpt2",
+    "get_num_threads", "set_num_threads", "popcnt", "ctz", "compute_rdms", "add_hci", "compute_enpt2", "compute_transition_rdms", "compute_overlap",
     "make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations",
     "device_count", "set_device", "nccl_unique_id", "init_comm", "launch_count", "reset_launch_count",
     "synchronize",

@@ -74,6 +74,8 @@ PROTOTYPES = {
     "pyci_op_get_element": (_i, [_vp, _l, _l, _vp]),
     "pyci_op_solve": (_i, [_vp, _l, _vp, _l, _l, _d, _vp, _vp, ctypes.POINTER(SolveStats)]),
     "pyci_compute_rdms": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "pyci_compute_transition_rdms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pyci_compute_overlap": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_d)]),
 }
 
 _LIB = None
@@ -302,3 +304,23 @@ def compute_rdms(ctx, wfn, kind, nbasis, coeffs):
     c = _f64(coeffs)
     check(lib().pyci_compute_rdms(ctx.handle, wfn.handle, _ptr(c), _ptr(r1), _ptr(r2)))
     return r1, r2
+
+
+def compute_transition_rdms(ctx, wfn1, wfn2, kind, nbasis, coeffs1, coeffs2):
+    n = nbasis
+    if kind == DOCI:
+        r1, r2 = np.empty((n, n)), np.empty((n, n))
+    elif kind == FULLCI:
+        r1, r2 = np.empty((2, n, n)), np.empty((3, n, n, n, n))
+    else:
+        r1, r2 = np.empty((n, n)), np.empty((n, n, n, n))
+    c1, c2 = _f64(coeffs1), _f64(coeffs2)
+    check(lib().pyci_compute_transition_rdms(ctx.handle, wfn1.handle, wfn2.handle, _ptr(c1), _ptr(c2), _ptr(r1), _ptr(r2)))
+    return r1, r2
+
+
+def compute_overlap(ctx, wfn1, wfn2, coeffs1, coeffs2):
+    c1, c2 = _f64(coeffs1), _f64(coeffs2)
+    out = _d(0.0)
+    check(lib().pyci_compute_overlap(ctx.handle, wfn1.handle, wfn2.handle, _ptr(c1), _ptr(c2), ctypes.byref(out)))
+    return out.value

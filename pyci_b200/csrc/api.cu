@@ -788,4 +788,20 @@ int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, 
     return rdms_impl(ctx, wfn, coeffs, rdm1, rdm2);
 }
 
+int pyci_compute_transition_rdms(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2, const double *coeffs1,
+                                 const double *coeffs2, double *rdm1, double *rdm2) {
+    if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !rdm1 || !rdm2)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(ctx));
+    return trdms_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, rdm1, rdm2);
+}
+
+int pyci_compute_overlap(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2, const double *coeffs1,
+                         const double *coeffs2, double *out) {
+    if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(ctx));
+    return overlap_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, out);
+}
+
 } // extern "C"

@@ -148,6 +148,10 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
 // rdm.cu
 int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2);
 
+int trdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2, const double *coeffs1, const double *coeffs2,
+               double *rdm1, double *rdm2);
+int overlap_impl(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wfn2, const double *coeffs1, const double *coeffs2,
+                 double *out);
 // hci.cu
 int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double eps, long *n_new,
                  double *seconds);

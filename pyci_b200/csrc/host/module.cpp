@@ -169,6 +169,19 @@ PYBIND11_MODULE(_pyci, m) {
           py::arg("wfn"), py::arg("coeffs"));
 
     // ---- pyci_b200 extensions: device context, row sharding, launch accounting
+    // compute_transition_rdms / compute_overlap (binding.cpp:1183-1206, 1293-1342)
+    m.def("compute_transition_rdms", [](const DOCIWfn &a, const DOCIWfn &b, const Array<double> c1, const Array<double> c2) { return py_compute_transition_rdms(a, b, c1, c2); },
+          py::arg("wfn1"), py::arg("wfn2"), py::arg("coeffs1"), py::arg("coeffs2"),
+          "Compute the transition one- and two- particle reduced density matrices of two wave functions (on the GPU).");
+    m.def("compute_transition_rdms", [](const FullCIWfn &a, const FullCIWfn &b, const Array<double> c1, const Array<double> c2) { return py_compute_transition_rdms(a, b, c1, c2); },
+          py::arg("wfn1"), py::arg("wfn2"), py::arg("coeffs1"), py::arg("coeffs2"));
+    m.def("compute_transition_rdms", [](const GenCIWfn &a, const GenCIWfn &b, const Array<double> c1, const Array<double> c2) { return py_compute_transition_rdms(a, b, c1, c2); },
+          py::arg("wfn1"), py::arg("wfn2"), py::arg("coeffs1"), py::arg("coeffs2"));
+    m.def("compute_overlap", [](const OneSpinWfn &a, const OneSpinWfn &b, const Array<double> c1, const Array<double> c2) { return py_compute_overlap(a, b, c1, c2); },
+          py::arg("wfn1"), py::arg("wfn2"), py::arg("coeffs1"), py::arg("coeffs2"),
+          "Compute the overlap of two wave functions (on the GPU).");
+    m.def("compute_overlap", [](const TwoSpinWfn &a, const TwoSpinWfn &b, const Array<double> c1, const Array<double> c2) { return py_compute_overlap(a, b, c1, c2); },
+          py::arg("wfn1"), py::arg("wfn2"), py::arg("coeffs1"), py::arg("coeffs2"));
     // add_hci / compute_enpt2 (binding.cpp:1147-1181, 1344-1375): same overloads, keywords and defaults
     m.def("add_hci", [](const SQuantOp &h, DOCIWfn &w, const Array<double> c, double eps, long nt) { return py_add_hci(h, w, c, eps, nt); },
           py::arg("ham"), py::arg("wfn"), py::arg("coeffs"), py::arg("eps") = 1.0e-5, py::arg("nthread") = -1,

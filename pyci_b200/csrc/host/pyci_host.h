@@ -203,6 +203,9 @@ struct SparseOp {
 };
 
 py::tuple py_compute_rdms(const Wfn &wfn, const Array<double> coeffs);
+py::tuple py_compute_transition_rdms(const Wfn &wfn1, const Wfn &wfn2, const Array<double> coeffs1,
+                                     const Array<double> coeffs2);
+double py_compute_overlap(const Wfn &wfn1, const Wfn &wfn2, const Array<double> coeffs1, const Array<double> coeffs2);
 long py_add_hci(const SQuantOp &ham, Wfn &wfn, const Array<double> coeffs, double eps, long nthread);
 double py_compute_enpt2(const SQuantOp &ham, const Wfn &wfn, const Array<double> coeffs, double energy, double eps,
                         long nthread);

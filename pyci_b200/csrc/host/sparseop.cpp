@@ -251,6 +251,57 @@ py::tuple py_compute_rdms(const Wfn &wfn, const Array<double> coeffs) {
     return py::make_tuple(r1, r2);
 }
 
+// py_compute_transition_rdms_{doci,fullci,genci} (rdm.cpp:1057-1088): shapes as compute_rdms
+py::tuple py_compute_transition_rdms(const Wfn &wfn1, const Wfn &wfn2, const Array<double> coeffs1,
+                                     const Array<double> coeffs2) {
+    if ((long)coeffs1.size() < wfn1.ndet || (long)coeffs2.size() < wfn2.ndet)
+        throw std::invalid_argument("coeffs has fewer elements than the wave function has determinants");
+    const long n = wfn1.nbasis;
+    Array<double> r1, r2;
+    switch (wfn1.kind()) {
+    case PYCI_DOCI:
+        r1 = Array<double>({n, n});
+        r2 = Array<double>({n, n});
+        break;
+    case PYCI_FULLCI:
+        r1 = Array<double>({2L, n, n});
+        r2 = Array<double>({3L, n, n, n, n});
+        break;
+    default:
+        r1 = Array<double>({n, n});
+        r2 = Array<double>({n, n, n, n});
+        break;
+    }
+    DeviceWfn d1(wfn1), d2(wfn2);
+    const double *c1 = coeffs1.data(), *c2 = coeffs2.data();
+    double *p1 = r1.mutable_data(), *p2 = r2.mutable_data();
+    pyci_ctx *ctx = device_context();
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_compute_transition_rdms(ctx, d1.w, d2.w, c1, c2, p1, p2);
+    }
+    check(rc);
+    return py::make_tuple(r1, r2);
+}
+
+// py_compute_overlap (overlap.cpp:60-76)
+double py_compute_overlap(const Wfn &wfn1, const Wfn &wfn2, const Array<double> coeffs1, const Array<double> coeffs2) {
+    if ((long)coeffs1.size() < wfn1.ndet || (long)coeffs2.size() < wfn2.ndet)
+        throw std::invalid_argument("coeffs has fewer elements than the wave function has determinants");
+    DeviceWfn d1(wfn1), d2(wfn2);
+    const double *c1 = coeffs1.data(), *c2 = coeffs2.data();
+    pyci_ctx *ctx = device_context();
+    double out = 0.0;
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        rc = pyci_compute_overlap(ctx, d1.w, d2.w, c1, c2, &out);
+    }
+    check(rc);
+    return out;
+}
+
 // py_add_hci (hci.cpp:282-301; binding.cpp:1147-1181): one heat-bath iteration on the device; the selected
 // determinants are read back and appended to the host wave function so that it stays the single owner of
 // the determinant list.  `nthread` is accepted for signature parity and ignored.

@@ -81,3 +81,13 @@ def sorted_rows(d):
         return d
     flat = d.reshape(d.shape[0], -1)
     return d[np.lexsort(flat.T[::-1])]
+
+
+@pytest.fixture(scope="session")
+def trdm_golden():
+    with np.load(os.path.join(GOLDEN, "trdm.npz")) as f:
+        return {k: f[k] for k in f.files}
+
+
+TRDM_CASES = [("h6_fullci", "fullci", 6, (3, 3)), ("lih_fullci", "fullci", 6, (2, 1)), ("be_doci", "doci", 14, (2, 2)),
+              ("h4_fullci", "fullci", 4, (2, 2))]

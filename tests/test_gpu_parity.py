@@ -582,3 +582,50 @@ def test_incremental_update_equals_fresh_build(pyci, kind, n, occ):
     op.close()
     ham.close()
     ctx.close()
+
+
+# ---- compute_transition_rdms / compute_overlap (rdm.cpp:634-1009, overlap.cpp) ---------------------------
+from conftest import TRDM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,kind,n,occ", TRDM_CASES)
+def test_transition_rdms_and_overlap(pyci, trdm_golden, tag, kind, n, occ):
+    g = {k: trdm_golden[f"{tag}.{k}"] for k in ("dets1", "dets2", "c1", "c2", "rdm1", "rdm2", "overlap")}
+    cls = getattr(pyci, kind + "_wfn")
+    w1, w2 = cls(n, occ[0], occ[1], g["dets1"]), cls(n, occ[0], occ[1], g["dets2"])
+    r1, r2 = pyci.compute_transition_rdms(w1, w2, g["c1"], g["c2"])
+    assert r1.shape == g["rdm1"].shape and r2.shape == g["rdm2"].shape
+    np.testing.assert_allclose(r1, g["rdm1"], rtol=0, atol=1e-13)   # fp64 atomics: summation order differs
+    np.testing.assert_allclose(r2, g["rdm2"], rtol=0, atol=1e-13)
+    assert abs(pyci.compute_overlap(w1, w2, g["c1"], g["c2"]) - float(g["overlap"])) <= 1e-13
+    assert abs(pyci.compute_overlap(w2, w1, g["c2"], g["c1"]) - float(g["overlap"])) <= 1e-13
+    s1, s2 = pyci.compute_transition_rdms(w1, w1, g["c1"], g["c1"])
+    q1, q2 = pyci.compute_rdms(w1, g["c1"])
+    np.testing.assert_allclose(s1, q1, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(s2, q2, rtol=0, atol=1e-13)
+    with pytest.raises(ValueError):
+        pyci.compute_transition_rdms(w1, w2, g["c1"][:-1], g["c2"])
+
+
+def test_transition_rdms_genci_equals_spinized_fullci(pyci):
+    """GenCI (intended semantics) on the spin-orbital images equals the spin-expanded FullCI transition RDMs; a
+    mismatched pair of spaces is refused."""
+    n, occ = 6, (3, 2)
+    full = pyci.fullci_wfn(n, *occ)
+    full.add_all_dets()
+    d = full.to_det_array()
+    d1, d2 = np.ascontiguousarray(d[::2]), np.ascontiguousarray(d[::3])
+    c1, c2 = seeded_vec(len(d1), 4), seeded_vec(len(d2), 6)
+    f1, f2 = pyci.compute_transition_rdms(pyci.fullci_wfn(n, occ[0], occ[1], d1), pyci.fullci_wfn(n, occ[0], occ[1], d2), c1, c2)
+    s1, s2 = pyci.spinize_rdms(f1, f2)
+    img = lambda x: np.ascontiguousarray((x[:, 0] | (x[:, 1] << np.uint64(n))).reshape(-1, 1))  # noqa: E731
+    g1, g2 = pyci.compute_transition_rdms(pyci.genci_wfn(2 * n, sum(occ), 0, img(d1)), pyci.genci_wfn(2 * n, sum(occ), 0, img(d2)), c1, c2)
+    o1, o2 = O.compute_transition_rdms(O.GENCI, 2 * n, sum(occ), 0, img(d1), img(d2), c1, c2)
+    np.testing.assert_allclose(g1, o1, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(g2, o2, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(g1, s1, rtol=0, atol=1e-13)
+    # spinize_rdms symmetrises the abab block into both orderings; compare the blocks the two conventions share
+    np.testing.assert_allclose(g2[:n, :n, :n, :n], s2[:n, :n, :n, :n], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(g2[n:, n:, n:, n:], s2[n:, n:, n:, n:], rtol=0, atol=1e-13)
+    with pytest.raises(ValueError):
+        pyci.compute_transition_rdms(pyci.fullci_wfn(n, 3, 2, d1), pyci.fullci_wfn(n, 2, 2), c1, c2)

@@ -187,3 +187,20 @@ def test_oracle_hci_genci_equals_fullci():
     ptf, ntf = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], fd, (one, two), c, -3.0, ecore, 1.0e-4)
     ptg, ntg = O.compute_enpt2(O.GENCI, 2 * n, sum(occ), 0, gd, (h2, g2), c, -3.0, ecore, 1.0e-4)
     assert ntf == ntg and abs(ptf - ptg) <= 1e-12 * abs(ptf)
+
+
+# ---- compute_transition_rdms / compute_overlap (rdm.cpp:634-1009, overlap.cpp) ---------------------------
+from conftest import TRDM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,kind,n,occ", TRDM_CASES)
+def test_oracle_transition_rdms_bit_exact(trdm_golden, tag, kind, n, occ):
+    g = {k: trdm_golden[f"{tag}.{k}"] for k in ("dets1", "dets2", "c1", "c2", "rdm1", "rdm2", "overlap")}
+    r1, r2 = O.compute_transition_rdms(KIND[kind], n, occ[0], occ[1], g["dets1"], g["dets2"], g["c1"], g["c2"])
+    assert np.array_equal(r1, g["rdm1"]) and np.array_equal(r2, g["rdm2"])
+    assert O.compute_overlap(g["dets1"], g["dets2"], g["c1"], g["c2"]) == float(g["overlap"])
+    # T(wfn, wfn, c, c) is the symmetric routine
+    s1, s2 = O.compute_transition_rdms(KIND[kind], n, occ[0], occ[1], g["dets1"], g["dets1"], g["c1"], g["c1"])
+    q1, q2 = O.compute_rdms(KIND[kind], n, occ[0], occ[1], g["dets1"], g["c1"])
+    np.testing.assert_allclose(s1, q1, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(s2, q2, rtol=0, atol=1e-13)
