@@ -343,6 +343,7 @@ void pyci_wfn_destroy(pyci_wfn *wfn) {
     ctx_activate(wfn->ctx);
     dev_free(wfn->dets);
     dev_free(wfn->slots);
+    dev_free(wfn->bloom);
     delete wfn;
 }
 

@@ -457,7 +457,7 @@ __global__ void uniform_counts(int *cnt, long n, int value) {
 
 template<int KM>
 __global__ void insert_kernel(typename SlotOf<KM>::type *slots, u32 mask, int shift, const u64 *dets,
-                              int nwords, long ndet) {
+                              int nwords, long ndet, u32 *bloom, u32 bmask) {
     const long idet = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idet >= ndet)
         return;
@@ -466,6 +466,10 @@ __global__ void insert_kernel(typename SlotOf<KM>::type *slots, u32 mask, int sh
     ix.slots = slots;
     ix.mask = mask;
     ix.shift = shift;
+    ix.bloom = nullptr;
+    ix.bmask = 0;
+    if (bloom)
+        bloom_set(bloom, bmask, ix.hash(a, b));
     u32 p;
     if constexpr (KM == KEY128)
         p = ix.home(a, b);
@@ -537,7 +541,7 @@ int build_index_t(pyci_wfn *wfn) {
     if (ndet > 0) {
         insert_kernel<KM><<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<slot_t *>(wfn->slots), wfn->mask,
                                                              (wfn->kind == PYCI_FULLCI) ? (int)wfn->nbasis : 0,
-                                                             wfn->dets, wfn->nwords, ndet);
+                                                             wfn->dets, wfn->nwords, ndet, wfn->bloom, wfn->bmask);
         ctx->launches++;
         int *bad = nullptr;
         const int init[2] = {0, 0x7fffffff};
@@ -932,6 +936,26 @@ int wfn_build_index(pyci_wfn *wfn) {
     PYCI_CUDA(dev_malloc(&wfn->slots, bytes));
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     PYCI_CUDA(cudaMemsetAsync(wfn->slots, 0xFF, bytes, ctx->stream));
+    // Slot tables beyond ~L2/2 are probed out of HBM (one random 32-byte sector per candidate; in a selected space
+    // nearly all of them miss): put a blocked Bloom filter in front, 8-32 bits per determinant (false positives
+    // <= 0.4 %), small enough to stay L2-resident.  PYCI_B200_BLOOM=0/1 forces it off / on.
+    dev_free(wfn->bloom);
+    wfn->bloom = nullptr;
+    wfn->bmask = 0;
+    {
+        const char *e = getenv("PYCI_B200_BLOOM");
+        const bool want = e ? atoi(e) != 0 : bytes > ((size_t)48 << 20);
+        if (want && wfn->ndet > 0) {
+            u64 words = 1024;
+            while (words < (u64)wfn->ndet / 2) // >= 16 bits per determinant ...
+                words <<= 1;
+            while (words * 4 > ((u64)64 << 20) && words / 2 >= (u64)wfn->ndet / 4) // ... down to 8 above 64 MB
+                words >>= 1;
+            PYCI_CUDA(dev_malloc(&wfn->bloom, sizeof(u32) * (size_t)words));
+            PYCI_CUDA(cudaMemsetAsync(wfn->bloom, 0, sizeof(u32) * (size_t)words, ctx->stream));
+            wfn->bmask = (u32)(words - 1);
+        }
+    }
     int rc;
     switch (wfn->keymode) {
     case KEY32:

@@ -83,6 +83,8 @@ struct pyci_wfn {
     u64 *dets = nullptr;   // [ndet][nwords]
     void *slots = nullptr; // hash slots (layout by keymode)
     u32 mask = 0;          // capacity-1 (capacity is a power of two)
+    u32 *bloom = nullptr;  // blocked Bloom filter over the keys (one 32-bit word per block, two bits per key), built
+    u32 bmask = 0;         // only when the slot table outgrows L2: a miss then costs an L2 hit instead of an HBM sector
     double hash_seconds = 0.0;
     double ext_seconds = 0.0; // device seconds of the last add_hci / compute_enpt2 walk over this wfn
 };
@@ -181,6 +183,17 @@ __device__ __forceinline__ u32 mix64(u64 h) {
     return (u32)h;
 }
 
+// Bloom probe of the determinant index: word and the two bits of a key from its 32-bit hash
+__device__ __forceinline__ bool bloom_pass(const u32 *__restrict__ bloom, u32 bmask, u32 h) {
+    const u32 g = h * 0x9e3779b1u;
+    const u32 w = __ldg(bloom + ((g >> 10) & bmask));
+    return ((w >> (g & 31u)) & (w >> ((g >> 5) & 31u)) & 1u) != 0u;
+}
+__device__ __forceinline__ void bloom_set(u32 *bloom, u32 bmask, u32 h) {
+    const u32 g = h * 0x9e3779b1u;
+    atomicOr(bloom + ((g >> 10) & bmask), (1u << (g & 31u)) | (1u << ((g >> 5) & 31u)));
+}
+
 struct __align__(8) Slot32 {
     u32 key;
     int val;
@@ -206,11 +219,17 @@ struct DetIndex<KEY32> {
     const Slot32 *slots;
     u32 mask;
     int shift;
+    const u32 *bloom;
+    u32 bmask;
     __device__ __forceinline__ u32 key(u64 a, u64 b) const { return (u32)a | ((u32)b << shift); }
+    __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix32(key(a, b)); }
     __device__ __forceinline__ u32 home(u32 k) const { return mix32(k) & mask; }
     __device__ __forceinline__ int find(u64 a, u64 b) const {
         const u32 k = key(a, b);
-        u32 p = home(k);
+        const u32 h = mix32(k);
+        if (bloom && !bloom_pass(bloom, bmask, h))
+            return -1;
+        u32 p = h & mask;
         for (;;) {
             const uint2 s = __ldg(reinterpret_cast<const uint2 *>(slots + p));
             if ((int)s.y < 0)
@@ -227,11 +246,17 @@ struct DetIndex<KEY64> {
     const Slot64 *slots;
     u32 mask;
     int shift;
+    const u32 *bloom;
+    u32 bmask;
     __device__ __forceinline__ u64 key(u64 a, u64 b) const { return a | (b << shift); }
+    __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix64(key(a, b)); }
     __device__ __forceinline__ u32 home(u64 k) const { return mix64(k) & mask; }
     __device__ __forceinline__ int find(u64 a, u64 b) const {
         const u64 k = key(a, b);
-        u32 p = home(k);
+        const u32 h = mix64(k);
+        if (bloom && !bloom_pass(bloom, bmask, h))
+            return -1;
+        u32 p = h & mask;
         for (;;) {
             const uint4 s = __ldg(reinterpret_cast<const uint4 *>(slots + p));
             if ((int)s.z < 0)
@@ -248,11 +273,15 @@ struct DetIndex<KEY128> {
     const Slot128 *slots;
     u32 mask;
     int shift;
-    __device__ __forceinline__ u32 home(u64 a, u64 b) const {
-        return mix64(a ^ (b * 0x9e3779b97f4a7c15ULL) ^ (b >> 29)) & mask;
-    }
+    const u32 *bloom;
+    u32 bmask;
+    __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix64(a ^ (b * 0x9e3779b97f4a7c15ULL) ^ (b >> 29)); }
+    __device__ __forceinline__ u32 home(u64 a, u64 b) const { return hash(a, b) & mask; }
     __device__ __forceinline__ int find(u64 a, u64 b) const {
-        u32 p = home(a, b);
+        const u32 h = hash(a, b);
+        if (bloom && !bloom_pass(bloom, bmask, h))
+            return -1;
+        u32 p = h & mask;
         for (;;) {
             const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(slots + p));
             const int v = __ldg(reinterpret_cast<const int *>(slots + p) + 4);

@@ -191,6 +191,8 @@ DetIndex<KM> make_index(const pyci_wfn *wfn) {
     ix.slots = reinterpret_cast<const typename SlotOf<KM>::type *>(wfn->slots);
     ix.mask = wfn->mask;
     ix.shift = (wfn->kind == PYCI_FULLCI) ? (int)wfn->nbasis : 0;
+    ix.bloom = wfn->bloom;
+    ix.bmask = wfn->bmask;
     return ix;
 }
 
