@@ -38,14 +38,18 @@ constexpr int UNROLL = 4;
 // every excitation a second time; rows with more hits than `cap` are enumerated again by the fill pass.
 template<int KIND, int KM>
 __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb, uint2 *hitlist,
-                                                    int cap) {
+                                                    int cap, u32 pair_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const RowTables T = carve_tables(smem_raw, nSa, nSb);
-    uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw + tables_bytes(nSa, nSb));
+    const RowTables T = carve_tables(smem_raw, nSa, nSb); // only the strings are allocated and used in this pass
+    uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw + table_strings_bytes(nSa, nSb));
     __shared__ RowShared rs;
     __shared__ int warp_sums[8];
     fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
+    if (KIND != PYCI_DOCI)
+        pair_masks_carve(rs, P, smem_raw + table_strings_bytes(nSa, nSb) + pair_bytes, nspin);
+    else
+        pair_masks_none(rs);
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
     for (long r = blockIdx.x; r < P.nloc; r += gridDim.x) {
@@ -55,23 +59,26 @@ __global__ void __launch_bounds__(256) count_kernel(BuildParams P, DetIndex<KM> 
         __syncthreads();
         if (KIND != PYCI_DOCI) {
             build_tables<KIND, false>(P, rs, T, nSa, nSb);
+            pair_masks_build(rs, P, pairs, nspin);
             __syncthreads();
         }
         uint2 *hrow = hitlist ? hitlist + (size_t)r * cap : nullptr;
         int cnt = 0;
         for (u32 base = 0; base < P.ncand; base += UNROLL * blockDim.x) {
             int hit[UNROLL];
+            u64 A[UNROLL], B[UNROLL];
+            bool want[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const u32 c = base + u * blockDim.x + threadIdx.x;
-                hit[u] = -1;
-                if (c < P.ncand) {
-                    u64 A, B;
+                want[u] = c < P.ncand;
+                A[u] = B[u] = 0ULL;
+                if (want[u]) {
                     double unused;
-                    candidate<KIND, false>(P, rs, T, pairs, c, A, B, unused);
-                    hit[u] = index.find(A, B);
+                    candidate<KIND, false>(P, rs, T, pairs, c, A[u], B[u], unused);
                 }
             }
+            find_batch<UNROLL>(index, A, B, want, hit);
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const bool keep = hit[u] >= 0 && hit[u] < P.ncol;
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
     uchar2 *pairs = reinterpret_cast<uchar2 *>(tbase + tables_bytes(nSa, nSb));
     __shared__ RowShared rs;
     __shared__ int low_count;
+    pair_masks_none(rs);
     fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
     const int lane = threadIdx.x & 31;
@@ -468,13 +476,10 @@ __global__ void insert_kernel(typename SlotOf<KM>::type *slots, u32 mask, int sh
     ix.shift = shift;
     ix.bloom = nullptr;
     ix.bmask = 0;
+    const u32 h = ix.hash(a, b);
     if (bloom)
-        bloom_set(bloom, bmask, ix.hash(a, b));
-    u32 p;
-    if constexpr (KM == KEY128)
-        p = ix.home(a, b);
-    else
-        p = ix.home(ix.key(a, b));
+        bloom_set(bloom, bmask, h);
+    u32 p = h & mask;
     for (;;) {
         // claim an empty slot (val == -1); keys are written afterwards -- determinants are unique, so
         // no key comparison is needed while inserting (verified by verify_kernel)
@@ -701,7 +706,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
         } else {
             const int block = pick_block((long)P.ncand / 4);
             int per_sm = 1;
-            const size_t csmem = tab_bytes + pair_bytes;
+            const size_t csmem = table_strings_bytes(nSa, nSb) + ((pair_bytes + 7) & ~(size_t)7) + pair_mask_bytes(P, KIND);
             if ((long)csmem > (long)ctx->smem_optin)
                 PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "excitation tables (%zu bytes) do not fit shared memory", csmem);
             PYCI_CUDA(cudaFuncSetAttribute(count_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
@@ -722,7 +727,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     PYCI_CUDA(dev_malloc(&hitlist, sizeof(uint2) * (size_t)nloc * (size_t)hitcap));
                 }
             }
-            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
+            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb, hitlist, hitcap,
+                                                                    (u32)((pair_bytes + 7) & ~(size_t)7));
             ctx->launches++;
         }
     }
@@ -949,7 +955,8 @@ int wfn_build_index(pyci_wfn *wfn) {
         const bool want = e ? atoi(e) != 0 : (!wfn->complete && wfn->ndet >= 4096);
         if (want && wfn->ndet > 0) {
             u64 words = 1024;
-            while (words < (u64)wfn->ndet / 2) // >= 16 bits per determinant ...
+            const u64 per = getenv("PYCI_B200_BLOOM_DIV") ? (u64)atoi(getenv("PYCI_B200_BLOOM_DIV")) : 2;
+            while (words < (u64)wfn->ndet / per) // >= 16 bits per determinant ...
                 words <<= 1;
             while (words * 4 > ((u64)64 << 20) && words / 2 >= (u64)wfn->ndet / 4) // ... down to 8 above 64 MB
                 words >>= 1;

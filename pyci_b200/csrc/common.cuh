@@ -223,12 +223,14 @@ struct DetIndex<KEY32> {
     u32 bmask;
     __device__ __forceinline__ u32 key(u64 a, u64 b) const { return (u32)a | ((u32)b << shift); }
     __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix32(key(a, b)); }
-    __device__ __forceinline__ u32 home(u32 k) const { return mix32(k) & mask; }
     __device__ __forceinline__ int find(u64 a, u64 b) const {
-        const u32 k = key(a, b);
-        const u32 h = mix32(k);
+        const u32 h = hash(a, b);
         if (bloom && !bloom_pass(bloom, bmask, h))
             return -1;
+        return probe(a, b, h);
+    }
+    __device__ __forceinline__ int probe(u64 a, u64 b, u32 h) const {
+        const u32 k = key(a, b);
         u32 p = h & mask;
         for (;;) {
             const uint2 s = __ldg(reinterpret_cast<const uint2 *>(slots + p));
@@ -249,13 +251,23 @@ struct DetIndex<KEY64> {
     const u32 *bloom;
     u32 bmask;
     __device__ __forceinline__ u64 key(u64 a, u64 b) const { return a | (b << shift); }
-    __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix64(key(a, b)); }
-    __device__ __forceinline__ u32 home(u64 k) const { return mix64(k) & mask; }
-    __device__ __forceinline__ int find(u64 a, u64 b) const {
+    // 32-bit mixing only (a 64-bit multiply is four to six instructions; the enumeration hashes 10^5 keys per row)
+    __device__ __forceinline__ u32 hash(u64 a, u64 b) const {
         const u64 k = key(a, b);
-        const u32 h = mix64(k);
+#ifdef PYCI_HASH_MIX64
+        return mix64(k);
+#else
+        return mix32((u32)k ^ ((u32)(k >> 32) * 0x9e3779b1u));
+#endif
+    }
+    __device__ __forceinline__ int find(u64 a, u64 b) const {
+        const u32 h = hash(a, b);
         if (bloom && !bloom_pass(bloom, bmask, h))
             return -1;
+        return probe(a, b, h);
+    }
+    __device__ __forceinline__ int probe(u64 a, u64 b, u32 h) const {
+        const u64 k = key(a, b);
         u32 p = h & mask;
         for (;;) {
             const uint4 s = __ldg(reinterpret_cast<const uint4 *>(slots + p));
@@ -275,12 +287,16 @@ struct DetIndex<KEY128> {
     int shift;
     const u32 *bloom;
     u32 bmask;
-    __device__ __forceinline__ u32 hash(u64 a, u64 b) const { return mix64(a ^ (b * 0x9e3779b97f4a7c15ULL) ^ (b >> 29)); }
-    __device__ __forceinline__ u32 home(u64 a, u64 b) const { return hash(a, b) & mask; }
+    __device__ __forceinline__ u32 hash(u64 a, u64 b) const {
+        return mix32((u32)a ^ ((u32)(a >> 32) * 0x9e3779b1u) ^ ((u32)b * 0x85ebca6bu) ^ ((u32)(b >> 32) * 0xc2b2ae35u));
+    }
     __device__ __forceinline__ int find(u64 a, u64 b) const {
         const u32 h = hash(a, b);
         if (bloom && !bloom_pass(bloom, bmask, h))
             return -1;
+        return probe(a, b, h);
+    }
+    __device__ __forceinline__ int probe(u64 a, u64 b, u32 h) const {
         u32 p = h & mask;
         for (;;) {
             const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(slots + p));
@@ -293,6 +309,32 @@ struct DetIndex<KEY128> {
         }
     }
 };
+
+// U lookups at once.  With the Bloom filter in place the U filter words are loaded back to back (independent loads
+// in flight) before any slot is probed: the enumeration of a selected space is bound by the latency of exactly that
+// load.  want[u] = false skips candidate u (out = -1).
+template<int U, class Index>
+__device__ __forceinline__ void find_batch(const Index &ix, const u64 (&A)[U], const u64 (&B)[U], const bool (&want)[U],
+                                           int (&out)[U]) {
+    if (ix.bloom) {
+        u32 h[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            h[u] = ix.hash(A[u], B[u]);
+            const u32 g = h[u] * 0x9e3779b1u;
+            w[u] = want[u] ? __ldg(ix.bloom + ((g >> 10) & ix.bmask)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 g = h[u] * 0x9e3779b1u;
+            out[u] = (((w[u] >> (g & 31u)) & (w[u] >> ((g >> 5) & 31u)) & 1u) != 0u) ? ix.probe(A[u], B[u], h[u]) : -1;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            out[u] = want[u] ? ix.find(A[u], B[u]) : -1;
+    }
+}
 
 // bits strictly between positions lo < hi of one 64-bit string
 __device__ __forceinline__ u64 between_mask(int lo, int hi) {

@@ -62,6 +62,8 @@ struct RowTables {
 };
 
 __host__ __device__ inline size_t tables_bytes(u32 nSa, u32 nSb) { return (size_t)24 * ((nSa + 1) & ~1u) + (size_t)24 * ((nSb + 1) & ~1u); }
+// the strings alone (all a pass that does not evaluate elements reads): they come first in the layout
+__host__ __device__ inline size_t table_strings_bytes(u32 nSa, u32 nSb) { return (size_t)8 * ((nSa + 1) & ~1u) + (size_t)8 * ((nSb + 1) & ~1u); }
 
 __device__ __forceinline__ RowTables carve_tables(unsigned char *base, u32 nSa, u32 nSb) {
     const u32 ea = (nSa + 1) & ~1u, eb = (nSb + 1) & ~1u;
@@ -89,8 +91,10 @@ __device__ __forceinline__ void build_tables(const BuildParams &P, const RowShar
             const long i = rs.occ[0][io], a = rs.vir[0][ia];
             const int par = parity_single(rs.det[0], (int)i, (int)a);
             T.sa_str[t] = rs.det[0] ^ (1ULL << i) ^ (1ULL << a);
-            T.sa_off[t] = (u32)(n3 * i + n1 * a);
-            T.sa_meta[t] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            if (VAL) { // VAL = false callers allocate the strings only (table_strings_bytes)
+                T.sa_off[t] = (u32)(n3 * i + n1 * a);
+                T.sa_meta[t] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            }
             if (VAL) { // sparseop.cpp:303-315 (GenCI :459-466)
                 const long ioff = n3 * i;
                 double val1 = __ldg(P.one_mo + n1 * i + a);
@@ -110,8 +114,10 @@ __device__ __forceinline__ void build_tables(const BuildParams &P, const RowShar
             const long i = rs.occ[1][io], a = rs.vir[1][ia];
             const int par = parity_single(rs.det[1], (int)i, (int)a);
             T.sb_str[tb] = rs.det[1] ^ (1ULL << i) ^ (1ULL << a);
-            T.sb_off[tb] = (u32)(n2 * i + a);
-            T.sb_meta[tb] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            if (VAL) {
+                T.sb_off[tb] = (u32)(n2 * i + a);
+                T.sb_meta[tb] = (u32)i | ((u32)a << 8) | ((u32)par << 16);
+            }
             if (VAL) { // sparseop.cpp:382-394
                 const long ioff = n3 * i;
                 double val1 = __ldg(P.one_mo + n1 * i + a);
@@ -161,6 +167,10 @@ __device__ __forceinline__ void candidate(const BuildParams &P, const RowShared 
     }
     if (c < P.nDa) { // sparseop.cpp:339-358 (GenCI :470-490)
         const u32 po = fdiv(c, P.dPva), pv = c - po * P.nPva;
+        if (!VAL && rs.pm[0][0] != nullptr) { // strings only: per-row pair masks
+            A ^= rs.pm[0][0][po] ^ rs.pm[0][1][pv];
+            return;
+        }
         const uchar2 o = pairs[po], v = pairs[pv];
         const long i = rs.occ[0][o.x], k = rs.occ[0][o.y], a = rs.vir[0][v.x], l = rs.vir[0][v.y];
         A ^= (1ULL << i) | (1ULL << k) | (1ULL << a) | (1ULL << l);
@@ -175,6 +185,10 @@ __device__ __forceinline__ void candidate(const BuildParams &P, const RowShared 
     if (KIND == PYCI_FULLCI) {
         if (c < P.nDb) { // sparseop.cpp:397-416
             const u32 po = fdiv(c, P.dPvb), pv = c - po * P.nPvb;
+            if (!VAL && rs.pm[1][0] != nullptr) {
+                B ^= rs.pm[1][0][po] ^ rs.pm[1][1][pv];
+                return;
+            }
             const uchar2 o = pairs[po], v = pairs[pv];
             const long i = rs.occ[1][o.x], k = rs.occ[1][o.y], a = rs.vir[1][v.x], l = rs.vir[1][v.y];
             B ^= (1ULL << i) | (1ULL << k) | (1ULL << a) | (1ULL << l);

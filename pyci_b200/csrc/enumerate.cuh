@@ -60,7 +60,61 @@ struct RowShared {
     int nocc[2];
     unsigned char occ[2][64];
     unsigned char vir[2][64];
+    // per-row masks of the same-spin double excitations (dynamic shared memory, or null): pm[spin][0][po] = bits of
+    // the occupied pair po, pm[spin][1][pv] = bits of the virtual pair pv; a double excitation is then two loads
+    // and two XORs instead of two pair look-ups, four orbital look-ups and four shifts
+    u64 *pm[2][2];
 };
+
+// bytes of the pair-mask tables of one CTA
+inline size_t pair_mask_bytes(const BuildParams &P, int kind) {
+    auto c2 = [](long m) { return (size_t)(m * (m - 1) / 2); };
+    const long va = P.n - P.nocc_a, vb = P.n - P.nocc_b;
+    size_t e = c2(P.nocc_a) + c2(va);
+    if (kind == PYCI_FULLCI)
+        e += c2(P.nocc_b) + c2(vb);
+    return 8 * (e + 4);
+}
+
+// carve the tables (once per CTA; thread 0) ...
+__device__ __forceinline__ void pair_masks_carve(RowShared &rs, const BuildParams &P, unsigned char *base, int nspin) {
+    if (threadIdx.x == 0) {
+        u64 *q = reinterpret_cast<u64 *>(base);
+        for (int s = 0; s < 2; ++s) {
+            const int no = s ? P.nocc_b : P.nocc_a, nv = P.n - no;
+            rs.pm[s][0] = rs.pm[s][1] = nullptr;
+            if (s < nspin) {
+                rs.pm[s][0] = q;
+                q += no * (no - 1) / 2;
+                rs.pm[s][1] = q;
+                q += nv * (nv - 1) / 2;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void pair_masks_none(RowShared &rs) {
+    if (threadIdx.x == 0)
+        rs.pm[0][0] = rs.pm[0][1] = rs.pm[1][0] = rs.pm[1][1] = nullptr;
+}
+
+// ... and fill them for the current row (after row_setup and a barrier; followed by a barrier)
+__device__ __forceinline__ void pair_masks_build(const RowShared &rs, const BuildParams &P, const uchar2 *__restrict__ pairs,
+                                                 int nspin) {
+    for (int s = 0; s < nspin; ++s) {
+        const int no = s ? P.nocc_b : P.nocc_a, nv = P.n - no;
+        const int npo = no * (no - 1) / 2, npv = nv * (nv - 1) / 2;
+        u64 *mo = rs.pm[s][0], *mv = rs.pm[s][1];
+        for (int t = threadIdx.x; t < npo + npv; t += blockDim.x) {
+            if (t < npo) {
+                const uchar2 o = pairs[t];
+                mo[t] = (1ULL << rs.occ[s][o.x]) | (1ULL << rs.occ[s][o.y]);
+            } else {
+                const uchar2 v = pairs[t - npo];
+                mv[t - npo] = (1ULL << rs.vir[s][v.x]) | (1ULL << rs.vir[s][v.y]);
+            }
+        }
+    }
+}
 
 // fill_occs / fill_virs (common.cpp:85-113) for one or two 64-bit strings, by warp 0
 __device__ __forceinline__ void row_setup(RowShared &rs, const BuildParams &P, long row, int nspin) {
@@ -162,6 +216,35 @@ __device__ __forceinline__ void decode(const BuildParams &P, const RowShared &rs
     }
 }
 
+
+// strings only (no excitation code): same-spin doubles through the per-row pair masks when they are there
+template<int KIND>
+__device__ __forceinline__ void decode_dets(const BuildParams &P, const RowShared &rs, const uchar2 *__restrict__ pairs,
+                                            u32 c, u64 &A, u64 &B) {
+    if (KIND != PYCI_DOCI && rs.pm[0][0] != nullptr) {
+        u32 d = c;
+        bool ok = true;
+        if (KIND == PYCI_FULLCI) {
+            ok = d >= P.nAB;
+            d -= P.nAB;
+        }
+        if (ok && d < P.nDa) {
+            const u32 po = fdiv(d, P.dPva), pv = d - po * P.nPva;
+            A = rs.det[0] ^ rs.pm[0][0][po] ^ rs.pm[0][1][pv];
+            B = rs.det[1];
+            return;
+        }
+        if (KIND == PYCI_FULLCI && ok && d - P.nDa < P.nDb) {
+            d -= P.nDa;
+            const u32 po = fdiv(d, P.dPvb), pv = d - po * P.nPvb;
+            A = rs.det[0];
+            B = rs.det[1] ^ rs.pm[1][0][po] ^ rs.pm[1][1][pv];
+            return;
+        }
+    }
+    u32 code;
+    decode<KIND>(P, rs, pairs, c, A, B, code);
+}
 
 __device__ __forceinline__ void fill_pairs(uchar2 *pairs, int m) {
     // pairs[y(y-1)/2 + x] = (x, y) for x < y < m

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) ext_walk_kernel(BuildParams P, DetIndex<K
     uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw + tables_bytes(nSa, nSb));
     __shared__ RowShared rs;
     __shared__ int s_over;
+    pair_masks_none(rs);
     fill_pairs(pairs, P.npairs_dim);
     constexpr int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
     constexpr bool TWO = (KIND == PYCI_FULLCI);
@@ -141,20 +142,22 @@ __global__ void __launch_bounds__(256) ext_walk_kernel(BuildParams P, DetIndex<K
             u64 A[EXT_UNROLL], B[EXT_UNROLL];
             double val[EXT_UNROLL];
             int hit[EXT_UNROLL];
+            bool want[EXT_UNROLL];
 #pragma unroll
             for (int u = 0; u < EXT_UNROLL; ++u) {
                 const u32 c = base + u * blockDim.x + threadIdx.x;
-                hit[u] = 0;
+                want[u] = false;
                 val[u] = 0.0;
+                A[u] = B[u] = 0ULL;
                 if (c < P.ncand) {
                     candidate<KIND, true>(P, rs, RT, pairs, c, A[u], B[u], val[u]);
-                    if (fabs(val[u]) > eps_i)
-                        hit[u] = index.find(A[u], B[u]);
+                    want[u] = fabs(val[u]) > eps_i;
                 }
             }
+            find_batch<EXT_UNROLL>(index, A, B, want, hit);
 #pragma unroll
             for (int u = 0; u < EXT_UNROLL; ++u) {
-                if (hit[u] >= 0)
+                if (!want[u] || hit[u] >= 0)
                     continue;
                 const long s = ext_slot<TWO>(T, A[u], B[u]);
                 if (s < 0)

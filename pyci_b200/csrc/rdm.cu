@@ -38,12 +38,19 @@ __device__ __forceinline__ void scatter4_diag(double *G, long n, long p, long q,
 constexpr int RDM_UNROLL = 4;
 
 template<int KIND, int KM>
-__global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> index) {
+__global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> index, u32 pair_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw);
     __shared__ RowShared rs;
     fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
+    // selected space (Bloom filter present): most candidates miss, so only the strings are formed up front (pair
+    // masks) and the excitation code is decoded for the hits
+    const bool lazy = KIND != PYCI_DOCI && index.bloom != nullptr;
+    if (lazy)
+        pair_masks_carve(rs, P, smem_raw + pair_bytes, nspin);
+    else
+        pair_masks_none(rs);
     const long n = P.n, n1 = n, n2 = n * n, n3 = n2 * n, n4 = n2 * n2;
     double *aa = P.rdm1, *bb = P.rdm1 + n2;
     double *aaaa = P.rdm2, *bbbb = P.rdm2 + n4, *abab = P.rdm2 + 2 * n4;
@@ -52,6 +59,10 @@ __global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> in
         __syncthreads();
         row_setup(rs, P, row, nspin);
         __syncthreads();
+        if (lazy) {
+            pair_masks_build(rs, P, pairs, nspin);
+            __syncthreads();
+        }
         const double ci = __ldg(P.coeffs + row);
         const double val1 = ci * ci;
         const int na = rs.nocc[0], nb = (KIND == PYCI_FULLCI) ? rs.nocc[1] : 0;
@@ -88,22 +99,31 @@ __global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> in
         for (u32 base = 0; base < P.ncand; base += RDM_UNROLL * blockDim.x) {
             int hit[RDM_UNROLL];
             u32 codes[RDM_UNROLL];
+            u64 A[RDM_UNROLL], B[RDM_UNROLL];
+            bool want[RDM_UNROLL];
 #pragma unroll
             for (int u = 0; u < RDM_UNROLL; ++u) {
                 const u32 c = base + u * blockDim.x + threadIdx.x;
-                hit[u] = -1;
+                want[u] = c < P.ncand;
                 codes[u] = 0;
-                if (c < P.ncand) {
-                    u64 A, B;
-                    decode<KIND>(P, rs, pairs, c, A, B, codes[u]);
-                    hit[u] = index.find(A, B);
+                A[u] = B[u] = 0ULL;
+                if (want[u]) {
+                    if (lazy)
+                        decode_dets<KIND>(P, rs, pairs, c, A[u], B[u]);
+                    else
+                        decode<KIND>(P, rs, pairs, c, A[u], B[u], codes[u]);
                 }
             }
+            find_batch<RDM_UNROLL>(index, A, B, want, hit);
 #pragma unroll
             for (int u = 0; u < RDM_UNROLL; ++u) {
                 if ((long)hit[u] <= row)
                     continue;
-                const u32 code = codes[u];
+                u32 code = codes[u];
+                if (lazy) {
+                    u64 a2, b2;
+                    decode<KIND>(P, rs, pairs, base + u * blockDim.x + threadIdx.x, a2, b2, code);
+                }
                 const int type = code >> 24;
                 const long i = (code >> 18) & 63, a = (code >> 12) & 63, k = (code >> 6) & 63, l = code & 63;
                 const double cc = ci * __ldg(P.coeffs + hit[u]);
@@ -168,14 +188,16 @@ __global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> in
 template<int KIND, int KM>
 int run_rdm(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P) {
     const DetIndex<KM> ix = make_index<KM>(wfn);
-    const size_t smem = pair_table_bytes(P);
+    const size_t pb = (pair_table_bytes(P) + 7) & ~(size_t)7;
+    const size_t smem = pb + pair_mask_bytes(P, KIND);
     const long work = (long)P.ncand / 4;
     const int block = work <= 256 ? 32 : work <= 1024 ? 64 : work <= 4096 ? 128 : 256;
     int per_sm = 1;
+    PYCI_CUDA(cudaFuncSetAttribute(rdm_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rdm_kernel<KIND, KM>, block, smem));
     const long grid = std::min<long>(P.nloc, (long)ctx->sm_count * std::max(per_sm, 1));
     if (grid > 0) {
-        rdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(P, ix);
+        rdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(P, ix, (u32)pb);
         ctx->launches++;
     }
     PYCI_CUDA(cudaGetLastError());
@@ -213,13 +235,19 @@ __device__ __forceinline__ void scatter4_dir(double *G, long n, long p, long q, 
 
 // P.coeffs = coefficients of wfn1, c2 = coefficients of wfn2
 template<int KIND, int KM>
-__global__ void __launch_bounds__(256) trdm_kernel(BuildParams P, DetIndex<KM> index2, const double *__restrict__ c2) {
+__global__ void __launch_bounds__(256) trdm_kernel(BuildParams P, DetIndex<KM> index2, const double *__restrict__ c2,
+                                                   u32 pair_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uchar2 *pairs = reinterpret_cast<uchar2 *>(smem_raw);
     __shared__ RowShared rs;
     __shared__ int self_hit;
     fill_pairs(pairs, P.npairs_dim);
     const int nspin = (KIND == PYCI_FULLCI) ? 2 : 1;
+    const bool lazy = KIND != PYCI_DOCI && index2.bloom != nullptr;
+    if (lazy)
+        pair_masks_carve(rs, P, smem_raw + pair_bytes, nspin);
+    else
+        pair_masks_none(rs);
     const long n = P.n, n1 = n, n2 = n * n, n3 = n2 * n, n4 = n2 * n2;
     double *aa = P.rdm1, *bb = P.rdm1 + n2;
     double *aaaa = P.rdm2, *bbbb = P.rdm2 + n4, *abab = P.rdm2 + 2 * n4;
@@ -230,6 +258,8 @@ __global__ void __launch_bounds__(256) trdm_kernel(BuildParams P, DetIndex<KM> i
         __syncthreads();
         if (threadIdx.x == 0)
             self_hit = index2.find(rs.det[0], rs.det[1]);
+        if (lazy)
+            pair_masks_build(rs, P, pairs, nspin);
         __syncthreads();
         const double ci = __ldg(P.coeffs + row);
         const double val1 = (self_hit >= 0) ? ci * __ldg(c2 + self_hit) : 0.0; // rdm.cpp:655-656,719-720
@@ -265,22 +295,31 @@ __global__ void __launch_bounds__(256) trdm_kernel(BuildParams P, DetIndex<KM> i
         for (u32 base = 0; base < P.ncand; base += RDM_UNROLL * blockDim.x) {
             int hit[RDM_UNROLL];
             u32 codes[RDM_UNROLL];
+            u64 A[RDM_UNROLL], B[RDM_UNROLL];
+            bool want[RDM_UNROLL];
 #pragma unroll
             for (int u = 0; u < RDM_UNROLL; ++u) {
                 const u32 c = base + u * blockDim.x + threadIdx.x;
-                hit[u] = -1;
+                want[u] = c < P.ncand;
                 codes[u] = 0;
-                if (c < P.ncand) {
-                    u64 A, B;
-                    decode<KIND>(P, rs, pairs, c, A, B, codes[u]);
-                    hit[u] = index2.find(A, B);
+                A[u] = B[u] = 0ULL;
+                if (want[u]) {
+                    if (lazy)
+                        decode_dets<KIND>(P, rs, pairs, c, A[u], B[u]);
+                    else
+                        decode<KIND>(P, rs, pairs, c, A[u], B[u], codes[u]);
                 }
             }
+            find_batch<RDM_UNROLL>(index2, A, B, want, hit);
 #pragma unroll
             for (int u = 0; u < RDM_UNROLL; ++u) {
                 if (hit[u] < 0)
                     continue;
-                const u32 code = codes[u];
+                u32 code = codes[u];
+                if (lazy) {
+                    u64 a2, b2;
+                    decode<KIND>(P, rs, pairs, base + u * blockDim.x + threadIdx.x, a2, b2, code);
+                }
                 const int type = code >> 24;
                 const long i = (code >> 18) & 63, a = (code >> 12) & 63, k = (code >> 6) & 63, l = code & 63;
                 const double cc = ci * __ldg(c2 + hit[u]);
@@ -371,14 +410,16 @@ __global__ void __launch_bounds__(256) overlap_kernel(DetIndex<KM> index2, const
 template<int KIND, int KM>
 int run_trdm(pyci_ctx *ctx, const pyci_wfn *wfn2, BuildParams &P, const double *c2) {
     const DetIndex<KM> ix = make_index<KM>(wfn2);
-    const size_t smem = pair_table_bytes(P);
+    const size_t pb = (pair_table_bytes(P) + 7) & ~(size_t)7;
+    const size_t smem = pb + pair_mask_bytes(P, KIND);
     const long work = (long)P.ncand / 4;
     const int block = work <= 256 ? 32 : work <= 1024 ? 64 : work <= 4096 ? 128 : 256;
     int per_sm = 1;
+    PYCI_CUDA(cudaFuncSetAttribute(trdm_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trdm_kernel<KIND, KM>, block, smem));
     const long grid = std::min<long>(P.nloc, (long)ctx->sm_count * std::max(per_sm, 1));
     if (grid > 0) {
-        trdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(P, ix, c2);
+        trdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(P, ix, c2, (u32)pb);
         ctx->launches++;
     }
     PYCI_CUDA(cudaGetLastError());
