@@ -15,7 +15,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 spec = bench.workload_spec(name)
 ham, wfn = bench.make_problem(pyci, spec)
 ctx = cabi.Context(0)
-kind = {"doci": cabi.DOCI, "fullci": cabi.FULLCI}[spec["kind"]]
+kind = {"doci": cabi.DOCI, "fullci": cabi.FULLCI, "genci": cabi.GENCI}[spec["kind"]]
 dham = cabi.Ham(ctx, ham.nbasis, ham.ecore, ham.one_mo, ham.two_mo, ham.h, ham.v, ham.w)
 dwfn = cabi.Wfn(ctx, kind, ham.nbasis, wfn.nocc_up, wfn.nocc_dn, wfn.to_det_array())
 op = cabi.Op(ctx, dham, dwfn)
@@ -25,6 +25,9 @@ x = np.random.default_rng(0).standard_normal(op.ncol)
 yref = None
 shapes = [(64, 4, 256, 2), (64, 4, 256, 3), (32, 2, 512, 2), (32, 2, 512, 3), (32, 2, 512, 4), (32, 1, 1024, 3),
           (64, 2, 512, 3), (32, 4, 256, 3)]
+if name == "cfg5" or (len(sys.argv) > 2 and sys.argv[2] == "short"):
+    shapes = [(1, 8, 256, 2), (1, 6, 256, 2), (32, 4, 256, 2), (-8, 3, 256, 2), (-8, 6, 256, 2), (-16, 2, 256, 2), (-16, 4, 256, 2),
+              (-32, 1, 256, 2), (-32, 2, 256, 2)]
 for tpr, ctas, blk, depth in shapes:
     if True:
         op.set_spmv_shape(tpr, ctas)
