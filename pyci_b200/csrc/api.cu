@@ -79,48 +79,6 @@ __global__ void export_lower_kernel(const long *__restrict__ indptr, const int *
     }
 }
 
-__global__ void prefix_from_counts(const int *cnt, long n, long *out) {
-    // single thread block sequential-by-chunks scan (export path only; n = rows of one shard)
-    __shared__ long carry;
-    __shared__ long ws[32];
-    if (threadIdx.x == 0)
-        carry = 0;
-    __syncthreads();
-    for (long base = 0; base < n; base += blockDim.x) {
-        const long i = base + threadIdx.x;
-        const long v = (i < n) ? cnt[i] : 0;
-        long x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const long t = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o)
-                x += t;
-        }
-        if ((threadIdx.x & 31) == 31)
-            ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            long t = (threadIdx.x < (blockDim.x >> 5)) ? ws[threadIdx.x] : 0;
-            for (int o = 1; o < 32; o <<= 1) {
-                const long q = __shfl_up_sync(0xffffffffu, t, o);
-                if (threadIdx.x >= o)
-                    t += q;
-            }
-            ws[threadIdx.x] = t;
-        }
-        __syncthreads();
-        const long woff = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
-        const long incl = x + woff + carry;
-        if (i < n)
-            out[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1)
-            carry = incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-        out[n] = carry;
-}
-
 } // namespace
 
 extern "C" {
@@ -553,8 +511,7 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
     long *outptr = nullptr;
     PYCI_CUDA(dev_malloc(&outptr, sizeof(long) * (size_t)(nloc + 1)));
     if (op->symmetric) {
-        prefix_from_counts<<<1, 1024, 0, st>>>(op->lowcnt, nloc, outptr);
-        ctx->launches++;
+        PYCI_TRY(scan_counts(ctx, op->lowcnt, nloc, outptr, nullptr)); // multi-block scan of the prefix counts
     } else {
         PYCI_CUDA(cudaMemcpyAsync(outptr, op->indptr, sizeof(long) * (nloc + 1), cudaMemcpyDeviceToDevice, st));
     }
