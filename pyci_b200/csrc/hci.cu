@@ -445,7 +445,12 @@ int walk_rows(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P, const OrderPar
     P.row0 = row0;
     P.nloc = nloc;
     const bool two = wfn->kind == PYCI_FULLCI;
-    long cap = std::max<long>(1L << 16, next_pow2(4 * std::max<long>(nloc, 1)));
+    // first guess: 64 external determinants per row (a heat-bath step typically multiplies the space by 10-50), within
+    // an eighth of the free memory; an overflowing pass is repeated with 4x the slots
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const long budget = std::max<long>(1L << 16, (long)(free_b / 8 / 24));
+    long cap = std::max<long>(1L << 16, next_pow2(std::min<long>(64 * std::max<long>(nloc, 1), budget) / 2 + 1));
     ExtBuffers E;
     for (;;) {
         if (cap > (1L << 31))
