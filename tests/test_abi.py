@@ -62,6 +62,13 @@ def test_compute_entry_points_fail_loudly_without_a_device():
         pyci.sparse_op(ham, wfn)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pyci.compute_rdms(wfn, np.ones(len(wfn)))
+    # the selected-CI, transition-RDM and overlap entry points are device-only as well
+    c = np.ones(len(wfn))
+    for call in (lambda: pyci.add_hci(ham, wfn, c), lambda: pyci.compute_enpt2(ham, wfn, c, 0.0),
+                 lambda: pyci.compute_transition_rdms(wfn, wfn, c, c), lambda: pyci.compute_overlap(wfn, wfn, c, c)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    assert len(wfn) == 2  # a failed add_hci leaves the host wave function untouched
 
 
 def test_product_package_never_imports_the_oracle():
