@@ -664,3 +664,67 @@ def test_bloom_filter_in_front_of_the_index(pyci, monkeypatch, kind, n, occ):
     ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
     oi, ox, od = O.sparse_op(okind, n, occ[0], occ[1], dets, ints)
     assert np.array_equal(b[0], oi) and np.array_equal(b[1], ox) and np.array_equal(b[2], od)
+
+
+def test_config3_full_size_properties(pyci):
+    """BASELINE config 3 at its full size (FullCI 14 orbitals 4a4b: 1 002 001 determinants, 2.2e9 stored entries) through
+    size-independent properties: entry counts from the combinatorial formulas, the first rows
+    bit-exact against the oracle, symmetry and linearity of the product, the eigen-residual of the solve, and the
+    traces / energy identity of the RDMs of that state."""
+    from math import comb
+
+    from pyci_b200 import cabi
+    n, occ = 14, (4, 4)
+    ecore, one, two = O.synthetic_integrals(n, 1234)
+    ham = pyci.hamiltonian(ecore, one, two)
+    wfn = pyci.fullci_wfn(n, *occ)
+    wfn.add_all_dets()
+    dets = wfn.to_det_array()
+    ndet = len(wfn)
+    assert ndet == comb(n, 4) ** 2 == 1002001
+    a, va = 4, n - 4
+    off = 2 * a * va + 2 * comb(a, 2) * comb(va, 2) + (a * va) ** 2  # connected determinants of every row
+    op = pyci.sparse_op(ham, wfn)
+    st = op.stats()
+    assert st["stored_nnz"] == ndet * (off + 1) == 2225444221 and st["fill_kernel"] == "fill_complete_kernel"
+    assert op.size == ndet * off // 2 + ndet == 1113223111  # lower triangle + diagonal
+    ip = op.indptr()
+    assert ip[0] == 0 and ip[-1] == op.size and np.all(np.diff(ip) >= 1) and ip.dtype == np.int64
+    # the first rows, every column, bit for bit (rectangular slice through the C ABI)
+    ctx = cabi.Context(0)
+    dham = cabi.Ham(ctx, n, ecore, one, two)
+    dwfn = cabi.Wfn(ctx, cabi.FULLCI, n, occ[0], occ[1], dets)
+    k = 48
+    head = cabi.Op(ctx, dham, dwfn, nrow=k, ncol=ndet, symmetric=False)
+    hi, hx, hd = head.export_csr()
+    oi, ox, od = O.sparse_op(O.FULLCI, n, occ[0], occ[1], dets, (one, two), nrow=k, ncol=ndet, symmetric=False)
+    assert np.array_equal(hi, oi) and np.array_equal(hx, ox) and np.array_equal(hd, od)
+    for i in (0, 7, k - 1):  # the symmetric operator holds the same lower-triangle elements
+        for j in hx[hi[i]:hi[i + 1]]:
+            if j <= i:
+                assert op.get_element(i, int(j)) == hd[hi[i] + int(np.searchsorted(hx[hi[i]:hi[i + 1]], j))]
+    head.close()
+    dwfn.close()
+    dham.close()
+    ctx.close()
+    # symmetry and linearity of y = A x
+    x, y = seeded_vec(ndet, 21), seeded_vec(ndet, 22)
+    ax, ay = op(x), op(y)
+    assert abs(y @ ax - x @ ay) <= 1e-11 * abs(y @ ax)
+    az = op(0.5 * x - 2.0 * y)
+    assert np.max(np.abs(az - (0.5 * ax - 2.0 * ay))) <= 1e-11 * np.max(np.abs(az))
+    # eigen-residual of the solve and the Rayleigh quotient
+    es, cs = op.solve(n=1, tol=1e-9)
+    c = cs[0]
+    hc = op(c)
+    e0 = es[0] - ecore
+    assert abs(c @ c - 1.0) <= 1e-10 and abs(c @ hc - e0 * (c @ c)) <= 1e-9
+    assert np.linalg.norm(hc - e0 * c) <= 1e-7 * abs(e0)
+    assert e0 < float(np.min([op.get_element(i, i) for i in range(0, 40)]))  # variational: below the lowest diagonals
+    # RDMs of that state: traces and the energy identity (test_routines.py:115-133)
+    d1, d2 = pyci.compute_rdms(wfn, c)
+    assert abs(np.trace(d1[0]) - occ[0]) <= 1e-10 and abs(np.trace(d1[1]) - occ[1]) <= 1e-10
+    h2, g2 = O.spin_orbital_integrals(one, two)
+    r1, r2 = pyci.spinize_rdms(d1, d2)
+    energy = ecore + np.einsum("ij,ij", h2, r1) + 0.25 * (np.einsum("ijkl,ijkl", g2, r2) - np.einsum("ijlk,ijkl", g2, r2))
+    assert abs(energy - es[0]) <= 1e-9
