@@ -41,6 +41,12 @@ void bind_spin_wfn(py::class_<W, Base> &c) {
     c.def("add_dets_from_wfn", [](W &w, const W &o) { w.add_dets_from(o); }, py::arg("wfn"),
           "Add the determinants of another wave function.");
     c.def("reserve", [](W &w, long n) { w.reserve(n); }, py::arg("n"), "Reserve space for ``n`` determinants.");
+    c.def("_append_new_dets", [](W &w, const Array<ulong> a) {
+        if (a.size() % w.nw)
+            throw std::invalid_argument("array size is not a multiple of the words per determinant");
+        w.append_new_dets(a.data(), (long)(a.size() / w.nw));
+    }, py::arg("dets"), "Bulk append of determinants known to be distinct and absent (what add_hci uses for the "
+                        "determinants selected on the device); no duplicate check.");
 }
 
 } // namespace

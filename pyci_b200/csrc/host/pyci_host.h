@@ -59,6 +59,9 @@ public:
     long find(const std::vector<ulong> &dets, const ulong *key) const;
     // map key -> idx, overwriting an existing mapping (dict[rank] = i); returns true if it was new
     bool assign(const std::vector<ulong> &dets, const ulong *key, long idx);
+    // map determinants [first, first + n) of dets, known to be distinct and absent from the table (the device's
+    // add_hci guarantees both), to their positions: no key comparisons, slots prefetched a block ahead
+    void insert_new_bulk(const std::vector<ulong> &dets, long first, long n);
     long size() const { return count_; }
 
 private:
@@ -117,6 +120,7 @@ struct Wfn {
     long index_det_from_rank(const Hash rank) const;
     Hash rank_det(const ulong *det) const { return spooky_rank(det, nw); }
     long add_det(const ulong *det);
+    void append_new_dets(const ulong *ptr, long n); // distinct determinants that are not in the wave function yet
     long add_det_from_occs(const long *occs);
     void add_hartreefock_det();
     void add_all_dets(long nthread);

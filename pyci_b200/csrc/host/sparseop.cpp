@@ -327,9 +327,7 @@ long py_add_hci(const SQuantOp &ham, Wfn &wfn, const Array<double> coeffs, doubl
     }
     check(rc);
     const long before = wfn.ndet;
-    wfn.reserve(before + nnew);
-    for (long i = 0; i < nnew; ++i)
-        wfn.add_det(&fresh[(size_t)(i * wfn.nw)]);
+    wfn.append_new_dets(fresh.data(), nnew); // distinct and absent by construction: no per-determinant look-up
     return wfn.ndet - before;
 }
 

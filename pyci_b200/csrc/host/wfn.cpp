@@ -108,6 +108,16 @@ long Wfn::add_det(const ulong *det) {
     return ndet++;
 }
 
+// Bulk form of add_det for determinants the caller guarantees to be distinct and new (py_add_hci: the device
+// de-duplicates and excludes the determinants already present).
+void Wfn::append_new_dets(const ulong *ptr, long n) {
+    if (n <= 0)
+        return;
+    dets.insert(dets.end(), ptr, ptr + (size_t)(n * nw));
+    dict.insert_new_bulk(dets, ndet, n);
+    ndet += n;
+}
+
 long Wfn::add_det_from_occs(const long *occs) {
     std::vector<ulong> det((size_t)nw, 0UL);
     fill_det(nocc_up, occs, &det[0]);

@@ -132,3 +132,29 @@ def test_utility_helpers_match_oracle_restatement():
     one, two = rng.standard_normal((n, n)), rng.standard_normal((n, n, n, n))
     for x, y in zip(pyci.make_senzero_integrals(one, two), O.senzero_integrals(one, two)):
         assert np.array_equal(x, y)
+
+
+def test_bulk_append_of_new_determinants():
+    """Wfn::append_new_dets, the host side of add_hci: determinants selected on the device (distinct, absent) are
+    appended without per-determinant look-ups; the dictionary then finds every determinant at its position and
+    still rejects duplicates."""
+    import numpy as np
+
+    import pyci_b200 as pyci
+    for cls, args, nw in ((pyci.fullci_wfn, (10, 3, 3), 2), (pyci.doci_wfn, (16, 4, 4), 1), (pyci.genci_wfn, (12, 5, 0), 1)):
+        full = cls(*args)
+        full.add_all_dets()
+        d = full.to_det_array()
+        d = np.ascontiguousarray(d[np.random.default_rng(3).permutation(len(d))])
+        for cut in (0, 1, len(d) // 3):
+            w = cls(*args, d[:cut]) if cut else cls(*args)
+            w._append_new_dets(d[cut:])
+            assert len(w) == len(d) and np.array_equal(w.to_det_array(), d)
+            for i in (0, cut, len(d) // 2, len(d) - 1):
+                assert w.index_det(d[i]) == i
+            assert w.add_det(d[len(d) // 2]) == -1 and len(w) == len(d)
+            w._append_new_dets(d[:0])  # empty append is a no-op
+            assert len(w) == len(d)
+        if nw > 1:  # a ragged array (not a whole number of determinants) is refused
+            with pytest.raises(ValueError):
+                cls(*args)._append_new_dets(np.zeros(2 * nw + 1, dtype=np.uint64))
