@@ -257,6 +257,44 @@ bool DetTable::assign(const std::vector<ulong> &dets, const ulong *key, long idx
     }
 }
 
+void DetTable::assign_bulk(const std::vector<ulong> &dets, long first, long n) {
+    if (n <= 0)
+        return;
+    long cap = std::max<long>(16, (long)slots_.size());
+    while (cap < 2 * (count_ + n))
+        cap <<= 1;
+    if (cap != (long)slots_.size())
+        grow(dets, cap);
+    const uint64_t mask = (uint64_t)cap - 1;
+    constexpr long B = 16;
+    uint64_t home[B];
+    for (long base = 0; base < n; base += B) {
+        const long m = std::min(B, n - base);
+        for (long j = 0; j < m; ++j) {
+            home[j] = mix(&dets[(first + base + j) * nw_], nw_) & mask;
+            __builtin_prefetch(&slots_[home[j]], 1);
+        }
+        for (long j = 0; j < m; ++j) {
+            const long idx = first + base + j;
+            const ulong *key = &dets[idx * nw_];
+            uint64_t p = home[j];
+            for (;;) {
+                const long s = slots_[p];
+                if (s < 0) {
+                    slots_[p] = idx;
+                    ++count_;
+                    break;
+                }
+                if (std::memcmp(&dets[s * nw_], key, sizeof(ulong) * nw_) == 0) {
+                    slots_[p] = idx;
+                    break;
+                }
+                p = (p + 1) & mask;
+            }
+        }
+    }
+}
+
 void DetTable::insert_new_bulk(const std::vector<ulong> &dets, long first, long n) {
     if (n <= 0)
         return;

@@ -62,6 +62,9 @@ public:
     // map determinants [first, first + n) of dets, known to be distinct and absent from the table (the device's
     // add_hci guarantees both), to their positions: no key comparisons, slots prefetched a block ahead
     void insert_new_bulk(const std::vector<ulong> &dets, long first, long n);
+    // assign() for determinants [first, first + n) in order (duplicates allowed: the later position wins), with
+    // the home slots prefetched a block ahead
+    void assign_bulk(const std::vector<ulong> &dets, long first, long n);
     long size() const { return count_; }
 
 private:
@@ -112,6 +115,7 @@ struct Wfn {
     void init(long nb, long nu, long nd, int nspin_);
     void load_file(const std::string &filename, int nspin_);
     void set_dets(long n, const ulong *ptr);
+    void set_new_dets(long n, const ulong *ptr);
     void set_occs(long n, const long *ptr);
 
     const ulong *det_ptr(long i) const { return &dets[i * nw]; }

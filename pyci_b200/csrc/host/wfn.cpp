@@ -69,9 +69,7 @@ void Wfn::set_dets(long n, const ulong *ptr) {
     ndet = n;
     dets.assign(ptr, ptr + n * nw);
     dict.reset(nw);
-    dict.reserve(n);
-    for (long i = 0; i < n; ++i)
-        dict.assign(dets, &dets[i * nw], i);
+    dict.assign_bulk(dets, 0, n);
 }
 
 // constructor from an occupation array: [n][nocc_up] or [n][2][nocc_up] (onespinwfn.cpp:65-78,
@@ -162,7 +160,7 @@ void Wfn::add_all_dets(long /*nthread*/) {
     std::vector<ulong> up, dn;
     colex_strings(nbasis, nocc_up, nword, maxrank_up, up);
     if (nspin == 1) {
-        set_dets(maxrank_up, up.data());
+        set_new_dets(maxrank_up, up.data());
         return;
     }
     colex_strings(nbasis, nocc_dn, nword, maxrank_dn, dn);
@@ -176,7 +174,15 @@ void Wfn::add_all_dets(long /*nthread*/) {
             std::memcpy(d, &up[a * nword], sizeof(ulong) * nword);
             std::memcpy(d + nword, &dn[b * nword], sizeof(ulong) * nword);
         }
-    set_dets(n, all.data());
+    set_new_dets(n, all.data());
+}
+
+// replace the contents by n determinants that are distinct by construction (add_all_dets): no key comparisons
+void Wfn::set_new_dets(long n, const ulong *ptr) {
+    ndet = n;
+    dets.assign(ptr, ptr + n * nw);
+    dict.reset(nw);
+    dict.insert_new_bulk(dets, 0, n);
 }
 
 // all e-fold excitations of one string, in the reference's order: outer loop over the colex
