@@ -204,3 +204,34 @@ def test_oracle_transition_rdms_bit_exact(trdm_golden, tag, kind, n, occ):
     q1, q2 = O.compute_rdms(KIND[kind], n, occ[0], occ[1], g["dets1"], g["c1"])
     np.testing.assert_allclose(s1, q1, rtol=0, atol=1e-13)
     np.testing.assert_allclose(s2, q2, rtol=0, atol=1e-13)
+
+
+def test_oracle_hci_enpt2_limits():
+    """Limits that hold for any implementation: a huge eps selects nothing, eps = 0 selects every connected external
+    determinant, a complete space has no external space (ENPT2 = E), zero coefficients select nothing."""
+    ecore, one, two = O.read_fcidump(datafile("h6_sto_3g"))
+    n, occ = one.shape[0], (3, 3)
+    full = O.all_dets(O.FULLCI, n, *occ)
+    c_full = seeded_vec(len(full), 1)
+    assert len(O.add_hci(O.FULLCI, n, occ[0], occ[1], full, (one, two), c_full, 0.0)) == 0
+    pt, nt = O.compute_enpt2(O.FULLCI, n, occ[0], occ[1], full, (one, two), c_full, -3.25, ecore, 0.0)
+    assert nt == 0 and pt == -3.25
+    sel = full[::5]
+    c = seeded_vec(len(sel), 2)
+    assert len(O.add_hci(O.FULLCI, n, occ[0], occ[1], sel, (one, two), c, 1.0e9)) == 0
+    assert len(O.add_hci(O.FULLCI, n, occ[0], occ[1], sel, (one, two), np.zeros(len(sel)), 1.0e-9)) == 0
+    # eps = 0 keeps every excitation with a non-zero element: a subset of the complement that contains every
+    # determinant the build would connect to the selection
+    everything = O.add_hci(O.FULLCI, n, occ[0], occ[1], sel, (one, two), c, 0.0)
+    have = {tuple(r) for r in sel.reshape(len(sel), -1).tolist()}
+    new = {tuple(r) for r in everything.reshape(len(everything), -1).tolist()}
+    assert not (new & have) and len(new) == len(everything)
+    ip, ix, dv = O.sparse_op(O.FULLCI, n, occ[0], occ[1], full, (one, two), symmetric=False)
+    pos = {tuple(r): i for i, r in enumerate(full.reshape(len(full), -1).tolist())}
+    rows = [pos[t] for t in have]
+    connected = set()
+    for r in rows:
+        for j, v in zip(ix[ip[r]:ip[r + 1]], dv[ip[r]:ip[r + 1]]):
+            if v != 0.0 and tuple(full[j].reshape(-1).tolist()) not in have:
+                connected.add(tuple(full[j].reshape(-1).tolist()))
+    assert new == connected
