@@ -128,6 +128,12 @@ PYCI_API double pyci_wfn_ext_seconds(const pyci_wfn *wfn);
  * With a communicator, rank r owns the contiguous row block r of ceil(nrow/nranks) rows. */
 PYCI_API int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
                   int symmetric, pyci_op **out);
+/* The row block that rank `rank` of `nranks` owns, built WITHOUT a communicator: construction has no collective
+ * (the reference's rows are independent, sparseop.cpp:196-199), so one process can build -- and check -- any shard
+ * of a row-sharded operator.  Export, pyci_op_get_element and pyci_op_matvec_dev (full x in, the shard's rows out)
+ * work on it; pyci_op_matvec / pyci_op_solve / pyci_op_update need the context's own layout (pyci_op_build). */
+PYCI_API int pyci_op_build_shard(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
+                        int symmetric, int rank, int nranks, pyci_op **out);
 PYCI_API void pyci_op_destroy(pyci_op *op);
 /* SparseOp::update (sparseop.cpp:175-201): grow a square symmetric operator built for the first op.nrow
  * determinants of wfn to all wfn.ndet of them (the caller appended determinants, e.g. with pyci_wfn_add_hci; the
@@ -149,6 +155,9 @@ PYCI_API long pyci_op_stored_nnz(const pyci_op *op);
 PYCI_API double pyci_op_ecore(const pyci_op *op);
 /* device seconds of the last build on this rank: [0] hash index, [1] count+scan, [2] fill+sort, [3] total */
 PYCI_API int pyci_op_build_times(const pyci_op *op, double *seconds4);
+/* device seconds of the fill kernel alone in the last build (CUDA events around its launch on the context's stream:
+ * the duration the roofline fraction of bench.py is computed from) */
+PYCI_API double pyci_op_fill_seconds(const pyci_op *op);
 /* name of the CUDA kernel that filled this operator (the dominant kernel of a construction; profiling aid --
  * the reference has one code path, SparseOp::add_row, sparseop.cpp:220-502) */
 PYCI_API const char *pyci_op_fill_kernel(const pyci_op *op);
@@ -157,6 +166,13 @@ PYCI_API const char *pyci_op_fill_kernel(const pyci_op *op);
  * layout: indptr[row_count+1] starting at 0, indices int64, data fp64, each row sorted by column
  * (sparseop.cpp:214-218). */
 PYCI_API int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data);
+
+/* The same export for a list of rows (global indices, all held by this rank; any order, repeats allowed): what
+ * py_indptr / py_indices / py_data would hold for those rows.  indptr[nrows+1] starts at 0.  indices / data may
+ * both be NULL to size the buffers first (indptr[nrows] = entries needed); cap = their capacity in entries.
+ * For operators whose whole export does not fit the host (configs 3-5) -- sampled-row parity checks. */
+PYCI_API int pyci_op_export_rows(pyci_op *op, long nrows, const long *rows, long cap, long *indptr, long *indices,
+                        double *data);
 
 /* SparseOp::perform_op (sparseop.cpp:96-112): y[nrow] = A x[ncol]; ecore is not applied.
  * Host buffers; with a communicator every rank passes the full x and receives the full y. */

@@ -40,6 +40,12 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_long, ctypes.c_long, ctypes.c_int,
             ctypes.POINTER(_c_long_p), ctypes.POINTER(_c_long_p), ctypes.POINTER(_c_double_p)]
+        L.oracle_sparse_op_rows.restype = ctypes.c_long
+        L.oracle_sparse_op_rows.argtypes = [
+            ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_int,
+            ctypes.POINTER(_c_long_p), ctypes.POINTER(_c_long_p), ctypes.POINTER(_c_double_p)]
         L.oracle_free.argtypes = [ctypes.c_void_p]
         L.oracle_matvec.argtypes = [ctypes.c_long] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + \
             [ctypes.c_void_p] * 2
@@ -170,25 +176,34 @@ def all_dets(kind, nbasis, nocc_up, nocc_dn=0):
 # the path
 
 
-def sparse_op(kind, nbasis, nocc_up, nocc_dn, dets, ints, nrow=-1, ncol=-1, symmetric=True):
+def sparse_op(kind, nbasis, nocc_up, nocc_dn, dets, ints, nrow=-1, ncol=-1, symmetric=True, rows=None):
     """Restates pyci.sparse_op(ham, wfn, nrow, ncol, symmetric) (sparseop.cpp:49-71,186-502).
     ints = (one_mo, two_mo) for FullCI/GenCI, (h, v, w) for DOCI.
+    rows: optional list of row indices -- row k of the result is row rows[k] of the operator (the reference's
+    row loop, sparseop.cpp:196-199, treats rows independently); nrow is then ignored.
     Returns (indptr int64[nrow+1], indices int64[nnz], data float64[nnz])."""
     L = lib()
     dets = np.ascontiguousarray(dets, dtype=np.uint64)
     ndet = dets.shape[0]
-    nrow = ndet if nrow < 0 else nrow
     ncol = ndet if ncol < 0 else ncol
+    if rows is not None:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        nrow = len(rows)
+    else:
+        nrow = ndet if nrow < 0 else nrow
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in ints] + [None]
     ip, ix, dv = _c_long_p(), _c_long_p(), _c_double_p()
-    nnz = L.oracle_sparse_op(kind, nbasis, nocc_up, nocc_dn, ndet, _p(dets), _p(arrs[0]), _p(arrs[1]),
-                             _p(arrs[2]), nrow, ncol, int(bool(symmetric)),
-                             ctypes.byref(ip), ctypes.byref(ix), ctypes.byref(dv))
+    nnz = L.oracle_sparse_op_rows(kind, nbasis, nocc_up, nocc_dn, ndet, _p(dets), _p(arrs[0]), _p(arrs[1]),
+                                  _p(arrs[2]), nrow, _p(rows), ncol, int(bool(symmetric)),
+                                  ctypes.byref(ip), ctypes.byref(ix), ctypes.byref(dv))
     if nnz < 0:
         raise MemoryError("oracle_sparse_op failed")
     indptr = np.ctypeslib.as_array(ip, shape=(nrow + 1,)).astype(np.int64, copy=True)
-    indices = np.ctypeslib.as_array(ix, shape=(max(nnz, 1),))[:nnz].astype(np.int64, copy=True)
-    data = np.ctypeslib.as_array(dv, shape=(max(nnz, 1),))[:nnz].astype(np.float64, copy=True)
+    if nnz > 0:
+        indices = np.ctypeslib.as_array(ix, shape=(nnz,)).astype(np.int64, copy=True)
+        data = np.ctypeslib.as_array(dv, shape=(nnz,)).astype(np.float64, copy=True)
+    else:
+        indices, data = np.zeros(0, dtype=np.int64), np.zeros(0)
     L.oracle_free(ip)
     L.oracle_free(ix)
     L.oracle_free(dv)

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "pyci_compute_enpt2": (_i, [_vp, _vp, _vp, _vp, _d, _d, ctypes.POINTER(_d), ctypes.POINTER(_l)]),
     "pyci_wfn_ext_seconds": (_d, [_vp]),
     "pyci_op_build": (_i, [_vp, _vp, _vp, _l, _l, _i, _vpp]),
+    "pyci_op_build_shard": (_i, [_vp, _vp, _vp, _l, _l, _i, _i, _i, _vpp]),
     "pyci_op_destroy": (None, [_vp]),
     "pyci_op_update": (_i, [_vp, _vp, _vp]),
     "pyci_op_nrow": (_l, [_vp]),
@@ -64,8 +65,10 @@ PROTOTYPES = {
     "pyci_op_stored_nnz": (_l, [_vp]),
     "pyci_op_ecore": (_d, [_vp]),
     "pyci_op_build_times": (_i, [_vp, _vp]),
+    "pyci_op_fill_seconds": (_d, [_vp]),
     "pyci_op_fill_kernel": (ctypes.c_char_p, [_vp]),
     "pyci_op_export_csr": (_i, [_vp, _vp, _vp, _vp]),
+    "pyci_op_export_rows": (_i, [_vp, _l, _vp, _l, _vp, _vp, _vp]),
     "pyci_op_matvec": (_i, [_vp, _vp, _vp]),
     "pyci_op_matvec_dev": (_i, [_vp, _vp, _vp]),
     "pyci_op_time_spmv": (_i, [_vp, _i, _i, _l, _vp]),
@@ -220,17 +223,27 @@ class Wfn:
 class Op:
     """pyci_op: CSR row shard resident in HBM."""
 
-    def __init__(self, ctx, ham, wfn, nrow=-1, ncol=-1, symmetric=True):
+    def __init__(self, ctx, ham, wfn, nrow=-1, ncol=-1, symmetric=True, shard=None):
+        """shard = (rank, nranks): that row block of the row-sharded operator, built without a communicator."""
         self.handle = ctypes.c_void_p()
-        check(lib().pyci_op_build(ctx.handle, ham.handle, wfn.handle, nrow, ncol, int(bool(symmetric)),
-                                  ctypes.byref(self.handle)))
+        if shard is None:
+            check(lib().pyci_op_build(ctx.handle, ham.handle, wfn.handle, nrow, ncol, int(bool(symmetric)),
+                                      ctypes.byref(self.handle)))
+        else:
+            check(lib().pyci_op_build_shard(ctx.handle, ham.handle, wfn.handle, nrow, ncol, int(bool(symmetric)),
+                                            int(shard[0]), int(shard[1]), ctypes.byref(self.handle)))
         self._refresh()
 
     def _refresh(self):
         L = lib()
         self.nrow, self.ncol = L.pyci_op_nrow(self.handle), L.pyci_op_ncol(self.handle)
         self.row_begin, self.row_count = L.pyci_op_row_begin(self.handle), L.pyci_op_row_count(self.handle)
-        self.size, self.stored_nnz = L.pyci_op_size(self.handle), L.pyci_op_stored_nnz(self.handle)
+        self.stored_nnz = L.pyci_op_stored_nnz(self.handle)
+
+    @property
+    def size(self):
+        """SparseOp::size of this rank's rows in the reference's storage (summed on the device at first use)"""
+        return lib().pyci_op_size(self.handle)
 
     def update(self, ham, wfn):
         """SparseOp::update: grow to all determinants now in wfn (incremental; square symmetric, one rank)."""
@@ -250,12 +263,26 @@ class Op:
     def fill_kernel(self):
         return lib().pyci_op_fill_kernel(self.handle).decode()
 
+    def fill_seconds(self):
+        return lib().pyci_op_fill_seconds(self.handle)
+
     def export_csr(self):
         indptr = np.empty(self.row_count + 1, dtype=np.int64)
         check(lib().pyci_op_export_csr(self.handle, _ptr(indptr), None, None))
         indices = np.empty(indptr[-1], dtype=np.int64)
         data = np.empty(indptr[-1], dtype=np.float64)
         check(lib().pyci_op_export_csr(self.handle, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def export_rows(self, rows):
+        """(indptr, indices, data) of the listed global rows in the reference's layout (pyci_op_export_rows)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+        check(lib().pyci_op_export_rows(self.handle, len(rows), _ptr(rows), 0, _ptr(indptr), None, None))
+        total = int(indptr[-1])
+        indices = np.empty(total, dtype=np.int64)
+        data = np.empty(total, dtype=np.float64)
+        check(lib().pyci_op_export_rows(self.handle, len(rows), _ptr(rows), total, _ptr(indptr), _ptr(indices), _ptr(data)))
         return indptr, indices, data
 
     def matvec(self, x, out=None):

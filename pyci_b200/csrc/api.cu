@@ -79,6 +79,33 @@ __global__ void export_lower_kernel(const long *__restrict__ indptr, const int *
     }
 }
 
+// rows[k] (global) -> first stored entry and number of exported entries (the col <= row prefix when `take` is given)
+__global__ void row_extent_kernel(const long *__restrict__ indptr, const int *__restrict__ take,
+                                  const long *__restrict__ rows, long row0, long nrows, long *__restrict__ src,
+                                  long *__restrict__ cnt) {
+    const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrows)
+        return;
+    const long r = rows[k] - row0;
+    src[k] = indptr[r];
+    cnt[k] = take ? (long)take[r] : indptr[r + 1] - indptr[r];
+}
+
+__global__ void export_rows_kernel(const long *__restrict__ src, const int *__restrict__ cols,
+                                   const double *__restrict__ vals, const long *__restrict__ outptr,
+                                   long *__restrict__ out_idx, double *__restrict__ out_val, long nrows) {
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long k = warp; k < nrows; k += nwarps) {
+        const long s0 = src[k], dst = outptr[k], cnt = outptr[k + 1] - dst;
+        for (long e = lane; e < cnt; e += 32) {
+            out_idx[dst + e] = cols[s0 + e];
+            out_val[dst + e] = vals[s0 + e];
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -134,7 +161,7 @@ int pyci_ctx_create(int device, void *stream, pyci_ctx **out) {
         unsigned long long keep = ~0ULL;
         PYCI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         PYCI_CUDA(cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
     return PYCI_OK;
@@ -145,7 +172,7 @@ void pyci_ctx_destroy(pyci_ctx *ctx) {
         return;
     cudaSetDevice(ctx->device);
     comm_destroy(ctx);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream)
@@ -309,8 +336,6 @@ int pyci_wfn_reindex(pyci_wfn *wfn) {
     if (!wfn)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     PYCI_TRY(ctx_activate(wfn->ctx));
-    PYCI_CUDA(dev_free(wfn->slots));
-    wfn->slots = nullptr;
     return wfn_build_index(wfn);
 }
 
@@ -341,6 +366,7 @@ int pyci_wfn_add_hci(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const do
     if (wfn->ndet == 0)
         return PYCI_OK;
     PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(wfn_ensure_index(wfn));
     PYCI_TRY(add_hci_impl(ctx, ham, wfn, coeffs, eps, n_new, &wfn->ext_seconds));
     if (*n_new > 0) {
         wfn->complete = (wfn->ndet == full_space_size(wfn->kind, wfn->nbasis, wfn->nocc_up, wfn->nocc_dn));
@@ -361,6 +387,7 @@ int pyci_compute_enpt2(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const 
         PYCI_FAIL(PYCI_ERR_VALUE, "compute_enpt2 of a DOCI wave function runs on its FullCI image (enpt2.cpp:376-380): "
                                   "upload the determinants as (d, d) FullCI strings");
     PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(wfn_ensure_index(wfn));
     return enpt2_impl(ctx, ham, wfn, coeffs, energy, eps, out, nterms, &wfn->ext_seconds);
 }
 
@@ -396,8 +423,8 @@ int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) 
 
 // ---- sparse operator -----------------------------------------------------------------------------
 
-int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol, int symmetric,
-                  pyci_op **out) {
+static int op_build_common(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol, int symmetric,
+                           int rank, int nranks, bool foreign, pyci_op **out) {
     if (!ctx || !ham || !wfn || !out)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     *out = nullptr;
@@ -419,10 +446,11 @@ int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long 
     op->ncol = ncol;
     op->symmetric = symmetric ? 1 : 0;
     op->ecore = ham->ecore;
-    const long R = ctx->nranks;
+    op->foreign = foreign;
+    const long R = nranks;
     op->npad = std::max<long>(1, (std::max(nrow, ncol) + R - 1) / R);
-    op->row0 = std::min(nrow, op->npad * ctx->rank);
-    op->nloc = std::min(nrow, op->npad * (ctx->rank + 1)) - op->row0;
+    op->row0 = std::min(nrow, op->npad * rank);
+    op->nloc = std::min(nrow, op->npad * (rank + 1)) - op->row0;
     int rc = PYCI_OK;
     auto alloc = [&](void **p, size_t bytes) {
         if (rc == PYCI_OK && dev_malloc(p, std::max<size_t>(bytes, 8)) != cudaSuccess) {
@@ -447,6 +475,23 @@ int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long 
     return PYCI_OK;
 }
 
+int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol, int symmetric,
+                  pyci_op **out) {
+    if (!ctx)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    return op_build_common(ctx, ham, wfn, nrow, ncol, symmetric, ctx->rank, ctx->nranks, false, out);
+}
+
+int pyci_op_build_shard(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol, int symmetric,
+                        int rank, int nranks, pyci_op **out) {
+    if (!ctx)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        PYCI_FAIL(PYCI_ERR_VALUE, "bad rank %d of %d", rank, nranks);
+    const bool foreign = !(rank == ctx->rank && nranks == ctx->nranks);
+    return op_build_common(ctx, ham, wfn, nrow, ncol, symmetric, rank, nranks, foreign, out);
+}
+
 int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn) {
     if (!op || !ham || !wfn)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
@@ -456,7 +501,7 @@ int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn) {
     if (wfn->ndet < op->nrow)
         PYCI_FAIL(PYCI_ERR_VALUE, "the wave function holds fewer determinants (%ld) than the operator has rows (%ld)",
                   wfn->ndet, op->nrow);
-    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1)
+    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1 || op->foreign)
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "incremental update needs a square symmetric operator on one rank: rebuild instead");
     if (wfn->kind == PYCI_DOCI ? (!ham->h || !ham->v || !ham->w) : (!ham->one_mo || !ham->two_mo))
         PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian lacks the integrals this wave-function kind needs");
@@ -483,7 +528,8 @@ long pyci_op_nrow(const pyci_op *op) { return op->nrow; }
 long pyci_op_ncol(const pyci_op *op) { return op->ncol; }
 long pyci_op_row_begin(const pyci_op *op) { return op->row0; }
 long pyci_op_row_count(const pyci_op *op) { return op->nloc; }
-long pyci_op_size(const pyci_op *op) { return op->size_ref; }
+long pyci_op_size(const pyci_op *op) { return op_size_ref(const_cast<pyci_op *>(op)); }
+double pyci_op_fill_seconds(const pyci_op *op) { return op ? op->fill_seconds : 0.0; }
 long pyci_op_stored_nnz(const pyci_op *op) { return op->nnz; }
 double pyci_op_ecore(const pyci_op *op) { return op->ecore; }
 
@@ -559,6 +605,63 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
     return rc;
 }
 
+int pyci_op_export_rows(pyci_op *op, long nrows, const long *rows, long cap, long *indptr, long *indices, double *data) {
+    if (!op || !indptr || (nrows > 0 && !rows) || nrows < 0)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    pyci_ctx *ctx = op->ctx;
+    PYCI_TRY(ctx_activate(ctx));
+    cudaStream_t st = ctx->stream;
+    indptr[0] = 0;
+    if (nrows == 0)
+        return PYCI_OK;
+    for (long k = 0; k < nrows; ++k)
+        if (rows[k] < op->row0 || rows[k] >= op->row0 + op->nloc)
+            PYCI_FAIL(PYCI_ERR_VALUE, "row %ld is not held by this rank (rows [%ld, %ld))", rows[k], op->row0,
+                      op->row0 + op->nloc);
+    long *drows = nullptr, *dsrc = nullptr, *dout = nullptr, *didx = nullptr;
+    double *dval = nullptr;
+    std::vector<long> hsrc((size_t)nrows), hcnt((size_t)nrows);
+    auto body = [&]() -> int {
+        PYCI_CUDA(dev_malloc(&drows, sizeof(long) * (size_t)nrows));
+        PYCI_CUDA(dev_malloc(&dsrc, sizeof(long) * (size_t)nrows));
+        PYCI_CUDA(dev_malloc(&dout, sizeof(long) * (size_t)(nrows + 1)));
+        PYCI_CUDA(cudaMemcpyAsync(drows, rows, sizeof(long) * (size_t)nrows, cudaMemcpyHostToDevice, st));
+        row_extent_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(op->indptr, op->symmetric ? op->lowcnt : nullptr,
+                                                                          drows, op->row0, nrows, dsrc, dout);
+        ctx->launches++;
+        PYCI_CUDA(cudaMemcpyAsync(hsrc.data(), dsrc, sizeof(long) * (size_t)nrows, cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaMemcpyAsync(hcnt.data(), dout, sizeof(long) * (size_t)nrows, cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        for (long k = 0; k < nrows; ++k)
+            indptr[k + 1] = indptr[k] + hcnt[(size_t)k];
+        const long total = indptr[nrows];
+        if (!indices && !data)
+            return PYCI_OK;
+        if (total > cap)
+            PYCI_FAIL(PYCI_ERR_VALUE, "the requested rows hold %ld entries, the output buffers %ld", total, cap);
+        if (total == 0)
+            return PYCI_OK;
+        PYCI_CUDA(cudaMemcpyAsync(dout, indptr, sizeof(long) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, st));
+        PYCI_CUDA(dev_malloc(&didx, sizeof(long) * (size_t)total));
+        PYCI_CUDA(dev_malloc(&dval, sizeof(double) * (size_t)total));
+        export_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(dsrc, op->cols, op->vals, dout, didx, dval, nrows);
+        ctx->launches++;
+        if (indices)
+            PYCI_CUDA(cudaMemcpyAsync(indices, didx, sizeof(long) * (size_t)total, cudaMemcpyDeviceToHost, st));
+        if (data)
+            PYCI_CUDA(cudaMemcpyAsync(data, dval, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        return PYCI_OK;
+    };
+    const int rc = body();
+    dev_free(drows);
+    dev_free(dsrc);
+    dev_free(dout);
+    dev_free(didx);
+    dev_free(dval);
+    return rc;
+}
+
 int pyci_op_matvec_dev(pyci_op *op, const double *x_dev, double *y_dev) {
     if (!op || !x_dev || !y_dev)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
@@ -575,6 +678,9 @@ int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
     PYCI_TRY(ctx_activate(ctx));
     if (op->symmetric && op->nrow != op->ncol)
         PYCI_FAIL(PYCI_ERR_TYPE, "symmetric operator must be square for matvec");
+    if (op->foreign)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "operator was built with pyci_op_build_shard for another rank layout: use "
+                                        "pyci_op_matvec_dev on its rows");
     const long R = ctx->nranks;
     if (!op->xbuf)
         PYCI_CUDA(dev_malloc(&op->xbuf, sizeof(double) * (size_t)std::max<long>(op->ncol, 1)));
@@ -709,6 +815,8 @@ int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long maxiter,
     PYCI_TRY(ctx_activate(ctx));
     if (stats)
         memset(stats, 0, sizeof(*stats));
+    if (op->foreign)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "operator was built with pyci_op_build_shard for another rank layout");
     const long nrow = op->nrow;
     // guards of SparseOp::solve_ci, sparseop.cpp:116-124
     if (n < 1 || (nrow > 1 && n >= nrow) || (nrow == 1 && n > 1))
@@ -743,6 +851,7 @@ int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, 
     if (!ctx || !wfn || !coeffs || !rdm1 || !rdm2)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(wfn_ensure_index(wfn));
     return rdms_impl(ctx, wfn, coeffs, rdm1, rdm2);
 }
 
@@ -751,6 +860,7 @@ int pyci_compute_transition_rdms(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci
     if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !rdm1 || !rdm2)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(wfn_ensure_index(wfn2));
     return trdms_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, rdm1, rdm2);
 }
 
@@ -759,6 +869,7 @@ int pyci_compute_overlap(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wf
     if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !out)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     PYCI_TRY(ctx_activate(ctx));
+    PYCI_TRY(wfn_ensure_index(wfn2));
     return overlap_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, out);
 }
 

@@ -525,13 +525,27 @@ __global__ void lookup_kernel(DetIndex<KM> ix, const u64 *dets, int nwords, long
     out[i] = ix.find(a, b);
 }
 
-__global__ void sorted_check_kernel(const u64 *dets, long ndet, int *unsorted) {
+// two-spin determinants: flags[0] |= 1 when (alpha, beta) does not strictly ascend (add_all_dets order,
+// twospinwfn.cpp:195-218; strictly ascending also means no duplicates); flags[1] = first determinant whose strings
+// do not hold the declared electrons inside nbasis orbitals (Wfn::init / add_det preconditions)
+__global__ void sorted_check_kernel(const u64 *dets, long ndet, u64 valid, int nocc_up, int nocc_dn, int *flags) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 >= ndet)
+    if (i >= ndet)
         return;
-    const u64 a0 = dets[2 * i], b0 = dets[2 * i + 1], a1 = dets[2 * i + 2], b1 = dets[2 * i + 3];
-    if (!(a0 < a1 || (a0 == a1 && b0 < b1)))
-        atomicOr(unsorted, 1);
+    const u64 a0 = dets[2 * i], b0 = dets[2 * i + 1];
+    if ((a0 & ~valid) || (b0 & ~valid) || __popcll(a0) != nocc_up || __popcll(b0) != nocc_dn)
+        atomicMin(flags + 1, (int)i);
+    if (i + 1 < ndet) {
+        const u64 a1 = dets[2 * i + 2], b1 = dets[2 * i + 3];
+        if (!(a0 < a1 || (a0 == a1 && b0 < b1)))
+            atomicOr(flags, 1);
+    }
+}
+
+__global__ void linear_indptr_kernel(long *indptr, long n, long m) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n)
+        indptr[i] = i * m;
 }
 
 size_t slot_bytes(int km) { return km == KEY32 ? sizeof(Slot32) : km == KEY64 ? sizeof(Slot64) : sizeof(Slot128); }
@@ -663,6 +677,7 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
                                                                                S.La, L1a);
     ctx->launches += 2;
     const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
+    PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
     if (with_slice) {
         PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fill_complete_kernel<true><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
@@ -670,6 +685,7 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
         PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         fill_complete_kernel<false><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     }
+    PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
     ctx->launches++;
     PYCI_CUDA(cudaGetLastError());
     free_string_tables(C.A); // stream-ordered: released after the fill has run
@@ -681,11 +697,21 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
 template<int KIND, int KM>
 int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, int npairs_dim) {
     cudaStream_t st = ctx->stream;
-    const DetIndex<KM> ix = make_index<KM>(wfn);
+    // The hash index of a complete sorted two-spin space is built lazily (wfn_build_index): its fill path takes the
+    // columns from colex ranks and never probes.  Every other path needs it now.
+    const bool may_skip_index = KIND == PYCI_FULLCI && wfn->complete && wfn->sorted2 && op->ncol == wfn->ndet &&
+                                !getenv("PYCI_B200_NO_COMPLETE_PATH") && !getenv("PYCI_B200_NO_SORTED_PATH") &&
+                                !getenv("PYCI_B200_FORCE_PROBE");
+    if (!may_skip_index)
+        PYCI_TRY(wfn_ensure_index(wfn));
+    DetIndex<KM> ix = make_index<KM>(wfn);
     const long nloc = op->nloc;
     const size_t pair_bytes = pair_table_bytes(P);
     // single-excitation tables live in shared memory (two-body kinds only)
-    const u32 nSa = (KIND == PYCI_DOCI) ? 0u : P.nSa, nSb = (KIND == PYCI_FULLCI && P.nAB > 0) ? P.nSb : 0u;
+    // (enum_params_init clamps an empty beta-single list to 1 for its divisions: pass the real count, which does not
+    // depend on whether alpha singles exist -- nocc_up == nbasis leaves nAB = 0 with beta singles still present)
+    const u32 nSa = (KIND == PYCI_DOCI) ? 0u : P.nSa,
+              nSb = (KIND == PYCI_FULLCI && P.nocc_b > 0 && P.n - P.nocc_b > 0) ? P.nSb : 0u;
     const size_t tab_bytes = tables_bytes(nSa, nSb);
 
     // block size from the amount of per-row work
@@ -698,12 +724,18 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     PYCI_CUDA(dev_malloc(&rowcnt, sizeof(int) * (size_t)(nloc + 1)));
     P.rowcnt = rowcnt;
     const bool analytic = wfn->complete && op->ncol == wfn->ndet;
-    if (nloc > 0) {
-        if (analytic) {
-            // complete space: every excitation is in the wfn, so each row holds ncand + 1 entries
-            uniform_counts<<<(unsigned)((nloc + 255) / 256), 256, 0, st>>>(rowcnt, nloc, (int)P.ncand + 1);
-            ctx->launches++;
-        } else {
+    long nnz = 0;
+    int maxrow = 0;
+    if (analytic) {
+        // complete space: every excitation is in the wave function, so each row holds ncand + 1 entries and the row
+        // pointer is a multiplication -- no count pass, no scan, nothing to read back
+        linear_indptr_kernel<<<(unsigned)((nloc + 256) / 256), 256, 0, st>>>(op->indptr, nloc, (long)P.ncand + 1);
+        ctx->launches++;
+        nnz = nloc * ((long)P.ncand + 1);
+        maxrow = nloc > 0 ? (int)P.ncand + 1 : 0;
+        PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
+    } else {
+        if (nloc > 0) {
             const int block = pick_block((long)P.ncand / 4);
             int per_sm = 1;
             const size_t csmem = table_strings_bytes(nSa, nSb) + ((pair_bytes + 7) & ~(size_t)7) + pair_mask_bytes(P, KIND);
@@ -731,29 +763,27 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                                                                     (u32)((pair_bytes + 7) & ~(size_t)7));
             ctx->launches++;
         }
+        // scan
+        const long nb = (nloc + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        long *blocksum = nullptr;
+        int *maxcnt = nullptr;
+        PYCI_CUDA(dev_malloc(&blocksum, sizeof(long) * (size_t)(nb + 2)));
+        PYCI_CUDA(dev_malloc(&maxcnt, sizeof(int)));
+        PYCI_CUDA(cudaMemsetAsync(maxcnt, 0, sizeof(int), st));
+        PYCI_CUDA(cudaMemsetAsync(op->indptr, 0, sizeof(long) * (size_t)(nloc + 1), st));
+        if (nloc > 0) {
+            scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(rowcnt, nloc, blocksum);
+            scan_of_sums<<<1, SCAN_BLOCK, 0, st>>>(blocksum, nb);
+            scan_finish<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(rowcnt, nloc, blocksum, op->indptr, maxcnt);
+            ctx->launches += 3;
+        }
+        PYCI_CUDA(cudaMemcpyAsync(&nnz, op->indptr + nloc, sizeof(long), cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaMemcpyAsync(&maxrow, maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        dev_free(blocksum);
+        dev_free(maxcnt);
     }
-    // scan
-    const long nb = (nloc + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    long *blocksum = nullptr;
-    int *maxcnt = nullptr;
-    PYCI_CUDA(dev_malloc(&blocksum, sizeof(long) * (size_t)(nb + 2)));
-    PYCI_CUDA(dev_malloc(&maxcnt, sizeof(int)));
-    PYCI_CUDA(cudaMemsetAsync(maxcnt, 0, sizeof(int), st));
-    PYCI_CUDA(cudaMemsetAsync(op->indptr, 0, sizeof(long) * (size_t)(nloc + 1), st));
-    if (nloc > 0) {
-        scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(rowcnt, nloc, blocksum);
-        scan_of_sums<<<1, SCAN_BLOCK, 0, st>>>(blocksum, nb);
-        scan_finish<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(rowcnt, nloc, blocksum, op->indptr, maxcnt);
-        ctx->launches += 3;
-    }
-    long nnz = 0;
-    int maxrow = 0;
-    PYCI_CUDA(cudaMemcpyAsync(&nnz, op->indptr + nloc, sizeof(long), cudaMemcpyDeviceToHost, st));
-    PYCI_CUDA(cudaMemcpyAsync(&maxrow, maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
-    PYCI_CUDA(cudaStreamSynchronize(st));
-    dev_free(blocksum);
-    dev_free(maxcnt);
     dev_free(rowcnt);
     P.rowcnt = nullptr;
 
@@ -772,6 +802,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
         P.sort_dbits = std::max(5, (bits + P.sort_passes - 1) / P.sort_passes);
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[2], st)); // after the allocations: ev[2]..ev[3] brackets kernels only
+    std::vector<u32> hb; // binomial table staged for the string-table pre-pass (lives until the final synchronise)
+    bool fill_timed = false;
     if (nloc > 0 && nnz > 0) {
         diag_kernel<KIND><<<(unsigned)((nloc + 127) / 128), 128, 0, st>>>(P);
         ctx->launches++;
@@ -789,7 +821,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 S.K1 = (u32)std::max(P.nocc_a, P.nocc_b) + 1;
                 S.M = P.ncand + 1;
                 S.Nb = (u32)Ub;
-                std::vector<u32> hb((size_t)P.n * S.K1);
+                hb.resize((size_t)P.n * S.K1);
                 for (int pp = 0; pp < P.n; ++pp)
                     for (u32 j = 0; j < S.K1; ++j)
                         hb[(size_t)pp * S.K1 + j] = (u32)std::min(binom_d(pp, j), 4294967295.0);
@@ -806,12 +838,20 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     int used = 0;
                     PYCI_TRY(run_complete(ctx, P, S, pair_bytes, &used));
                     done = used != 0;
-                    if (done)
+                    if (done) {
                         op->fill_kernel = "fill_complete_kernel";
+                        fill_timed = true;
+                    }
                 }
                 if (!done && (long)smem <= (long)ctx->smem_optin) {
+                    if (!direct) {
+                        PYCI_TRY(wfn_ensure_index(wfn));
+                        ix = make_index<KM>(wfn);
+                    }
                     int per_sm = 1;
                     long grid;
+                    PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
+                    fill_timed = true;
                     if (direct) {
                         PYCI_CUDA(cudaFuncSetAttribute(fill_sorted_kernel<KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sorted_kernel<KM, true>, block, smem));
@@ -823,16 +863,17 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                         grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
                         fill_sorted_kernel<KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, S, nSa, nSb);
                     }
+                    PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
                     ctx->launches++;
                     done = true;
                     op->fill_kernel = "fill_sorted_kernel";
                 }
-                // hb stays alive until the copy is consumed: the stream is synchronised below
-                PYCI_CUDA(cudaStreamSynchronize(st));
-                dev_free(dbinom);
+                dev_free(dbinom); // stream-ordered; hb outlives the copy (synchronised at the end of the build)
             }
         }
         if (!done) {
+            PYCI_TRY(wfn_ensure_index(wfn));
+            ix = make_index<KM>(wfn);
             int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
             size_t smem = 0;
             for (;;) { // keys (ping-pong) + values + radix counters + tables + pair table
@@ -849,6 +890,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             // most candidates miss (selected space): evaluate elements for hits only
             const bool lazy = !analytic && (double)nnz < 0.25 * (double)nloc * ((double)P.ncand + 1.0);
             int per_sm = 1;
+            PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
+            fill_timed = true;
             if (lazy) {
                 PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, true>, block, smem));
@@ -860,6 +903,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
                 fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
             }
+            PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
             ctx->launches++;
             op->fill_kernel = "fill_kernel";
         }
@@ -868,13 +912,16 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     dev_free(hitlist);
     PYCI_CUDA(cudaStreamSynchronize(st));
     PYCI_CUDA(cudaGetLastError());
-    float ms01 = 0, ms12 = 0;
+    float ms01 = 0, ms12 = 0, ms45 = 0;
     cudaEventElapsedTime(&ms01, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms12, ctx->ev[2], ctx->ev[3]);
+    if (fill_timed)
+        cudaEventElapsedTime(&ms45, ctx->ev[4], ctx->ev[5]);
     op->times[0] = wfn->hash_seconds;
     op->times[1] = ms01 * 1e-3;
     op->times[2] = ms12 * 1e-3;
     op->times[3] = op->times[1] + op->times[2];
+    op->fill_seconds = fill_timed ? ms45 * 1e-3 : op->times[2];
     return PYCI_OK;
 }
 
@@ -905,6 +952,29 @@ __global__ void lowcnt_sum_kernel(const int *lowcnt, long n, unsigned long long 
 
 } // namespace
 
+long op_size_ref(pyci_op *op) {
+    if (op->size_ref >= 0)
+        return op->size_ref;
+    pyci_ctx *ctx = op->ctx;
+    if (ctx_activate(ctx) != PYCI_OK)
+        return -1;
+    unsigned long long *acc = nullptr, h = 0;
+    if (dev_malloc(&acc, sizeof(unsigned long long)) != cudaSuccess)
+        return -1;
+    cudaMemsetAsync(acc, 0, sizeof(unsigned long long), ctx->stream);
+    if (op->nloc > 0) {
+        lowcnt_sum_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(op->lowcnt, op->nloc, acc);
+        ctx->launches++;
+    }
+    cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    dev_free(acc);
+    if (e != cudaSuccess)
+        return -1;
+    op->size_ref = (long)h;
+    return op->size_ref;
+}
+
 // indptr[0..n] = exclusive int64 scan of cnt[0..n) (indptr[n] = total); *maxcnt (device, may be null) = max cnt
 int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt) {
     cudaStream_t st = ctx->stream;
@@ -929,7 +999,8 @@ int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt
     return PYCI_OK;
 }
 
-int wfn_build_index(pyci_wfn *wfn) {
+// The hash index itself (slots + Bloom filter): insert, verify.
+static int wfn_build_hash(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
     // capacity: power of two with load factor in (0.25, 0.5]
     u64 cap = 16;
@@ -937,6 +1008,9 @@ int wfn_build_index(pyci_wfn *wfn) {
         cap <<= 1;
     if (cap > (1ULL << 31))
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "too many determinants for the device index (%ld)", wfn->ndet);
+    dev_free(wfn->slots);
+    wfn->slots = nullptr;
+    wfn->index_valid = false;
     wfn->mask = (u32)(cap - 1);
     const size_t bytes = slot_bytes(wfn->keymode) * (size_t)cap;
     PYCI_CUDA(dev_malloc(&wfn->slots, bytes));
@@ -978,30 +1052,64 @@ int wfn_build_index(pyci_wfn *wfn) {
         break;
     }
     PYCI_TRY(rc);
-    wfn->sorted2 = false;
-    if (wfn->kind == PYCI_FULLCI && wfn->ndet > 0) {
-        int *flag = nullptr, h = 1;
-        PYCI_CUDA(dev_malloc(&flag, sizeof(int)));
-        PYCI_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-        sorted_check_kernel<<<(unsigned)((wfn->ndet + 255) / 256), 256, 0, ctx->stream>>>(wfn->dets, wfn->ndet, flag);
-        ctx->launches++;
-        PYCI_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
-        dev_free(flag);
-        wfn->sorted2 = (h == 0);
-    }
     PYCI_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    wfn->hash_seconds = ms * 1e-3;
+    wfn->hash_seconds += ms * 1e-3;
+    wfn->index_valid = true;
     return PYCI_OK;
+}
+
+int wfn_ensure_index(const pyci_wfn *wfn) {
+    if (wfn->index_valid)
+        return PYCI_OK;
+    return wfn_build_hash(const_cast<pyci_wfn *>(wfn)); // a cache: logically const
+}
+
+// Validation + index of a wave function whose determinants are resident.  Two-spin determinants are first checked for
+// add_all_dets order and occupations in one pass; a COMPLETE space in that order needs nothing else -- strictly
+// ascending strings are unique, and its construction path (build_complete.cuh) derives columns from colex ranks --
+// so its hash index is deferred until something probes it (wfn_ensure_index: index_det, RDMs, add_hci, the general
+// fill paths).  Every other wave function gets its hash index here (insert + verify: duplicates, occupations).
+int wfn_build_index(pyci_wfn *wfn) {
+    pyci_ctx *ctx = wfn->ctx;
+    dev_free(wfn->slots);
+    wfn->slots = nullptr;
+    wfn->index_valid = false;
+    wfn->sorted2 = false;
+    wfn->hash_seconds = 0.0;
+    if (wfn->kind == PYCI_FULLCI && wfn->ndet > 0) {
+        int *flags = nullptr, h[2] = {1, 0x7fffffff};
+        const int init[2] = {0, 0x7fffffff};
+        PYCI_CUDA(dev_malloc(&flags, 2 * sizeof(int)));
+        PYCI_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        PYCI_CUDA(cudaMemcpyAsync(flags, init, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        const u64 valid = (wfn->nbasis >= 64) ? ~0ULL : ((1ULL << wfn->nbasis) - 1ULL);
+        sorted_check_kernel<<<(unsigned)((wfn->ndet + 255) / 256), 256, 0, ctx->stream>>>(
+            wfn->dets, wfn->ndet, valid, (int)wfn->nocc_up, (int)wfn->nocc_dn, flags);
+        ctx->launches++;
+        PYCI_CUDA(cudaMemcpyAsync(h, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PYCI_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(flags);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        wfn->hash_seconds = ms * 1e-3;
+        if (h[1] != 0x7fffffff)
+            PYCI_FAIL(PYCI_ERR_VALUE, "determinant %d does not have the declared occupation", h[1]);
+        wfn->sorted2 = (h[0] == 0);
+        if (wfn->complete && wfn->sorted2 && !getenv("PYCI_B200_EAGER_INDEX"))
+            return PYCI_OK;
+    }
+    return wfn_build_hash(wfn);
 }
 
 int wfn_index_dets_impl(pyci_wfn *wfn, long n, const u64 *dets_dev, long *out_dev) {
     pyci_ctx *ctx = wfn->ctx;
     if (n <= 0)
         return PYCI_OK;
+    PYCI_TRY(wfn_ensure_index(wfn));
     const unsigned blocks = (unsigned)((n + 255) / 256);
     switch (wfn->keymode) {
     case KEY32:
@@ -1045,22 +1153,7 @@ int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_
         rc = dispatch_key<PYCI_GENCI>(ctx, wfn, op, P, npairs_dim);
     PYCI_TRY(rc);
 
-    // SparseOp::size in the reference's storage
-    if (op->symmetric) {
-        unsigned long long *acc = nullptr;
-        PYCI_CUDA(dev_malloc(&acc, sizeof(unsigned long long)));
-        PYCI_CUDA(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), ctx->stream));
-        if (op->nloc > 0) {
-            lowcnt_sum_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(op->lowcnt, op->nloc, acc);
-            ctx->launches++;
-        }
-        unsigned long long h = 0;
-        PYCI_CUDA(cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-        PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
-        dev_free(acc);
-        op->size_ref = (long)h;
-    } else {
-        op->size_ref = op->nnz;
-    }
+    // SparseOp::size in the reference's storage: summed from lowcnt on first use (op_size_ref)
+    op->size_ref = op->symmetric ? -1 : op->nnz;
     return PYCI_OK;
 }

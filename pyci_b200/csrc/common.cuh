@@ -55,7 +55,7 @@ struct pyci_ctx {
     long launches = 0;
     int sm_count = 148;
     int smem_optin = 0; // max dynamic shared memory per block (opt-in)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct pyci_ham {
@@ -82,6 +82,7 @@ struct pyci_wfn {
     bool sorted2 = false;  // two-spin determinants ascend in (alpha, beta) as integers (add_all_dets order)
     u64 *dets = nullptr;   // [ndet][nwords]
     void *slots = nullptr; // hash slots (layout by keymode)
+    bool index_valid = false; // slots / bloom hold the current determinants (built lazily for complete sorted spaces)
     u32 mask = 0;          // capacity-1 (capacity is a power of two)
     u32 *bloom = nullptr;  // blocked Bloom filter over the keys (one 32-bit word per block, two bits per key), built
     u32 bmask = 0;         // only when the slot table outgrows L2: a miss then costs an L2 hit instead of an HBM sector
@@ -95,6 +96,7 @@ struct pyci_op {
     long row0 = 0, nloc = 0; // this rank's rows [row0, row0+nloc)
     long npad = 0;           // rows per rank (uniform), npad*nranks >= nrow
     int symmetric = 0;
+    bool foreign = false;    // built by pyci_op_build_shard for a rank layout other than the context's: no collectives
     double ecore = 0.0;
     long nnz = 0;            // stored non-zeros (full rows)
     long size_ref = 0;       // SparseOp::size in the reference's storage for these rows
@@ -104,6 +106,7 @@ struct pyci_op {
     int *lowcnt = nullptr;   // [nloc] entries with col <= row (sorted rows => a prefix)
     double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
     double times[4] = {0, 0, 0, 0};
+    double fill_seconds = 0.0; // device seconds of the fill kernel alone (CUDA events around its launch)
     const char *fill_kernel = "none"; // which fill path built this operator
     int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use;
                                      // spmv_tpr < 0: bulk-copy stream kernel with -spmv_tpr warps per CTA, ring depth spmv_ctas
@@ -138,6 +141,8 @@ int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
 
 // build.cu
 int wfn_build_index(pyci_wfn *wfn);
+int wfn_ensure_index(const pyci_wfn *wfn); // builds the hash index if it was deferred
+long op_size_ref(pyci_op *op);             // SparseOp::size of this rank's rows (lazily summed)
 int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
 int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt);
 // update.cu

@@ -659,6 +659,7 @@ int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double
         wfn->complete = false; // re-derived below
         dev_free(wfn->slots);
         wfn->slots = nullptr;
+        wfn->index_valid = false;
         return PYCI_OK;
     };
     int rc = body();

@@ -245,7 +245,7 @@ int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci
         op->nloc = n1;
         op->npad = std::max<long>(1, n1);
         op->nnz = total;
-        op->size_ref += T.size_ref;
+        op->size_ref = -1; // summed again from the grown lowcnt on first use
         op->ecore = ham->ecore;
         op->fill_kernel = T.fill_kernel;
         return PYCI_OK;

@@ -40,6 +40,33 @@ def test_oracle_small_csr_bit_exact(small, fn, kind, occ):
     assert abs(e0 + ecore - float(small[tag + ".E0"])) < 1e-10
 
 
+@pytest.mark.parametrize("fn,kind,occ", SMALL[:4] + SMALL[4:5])
+def test_oracle_row_list_equals_reference_rows(small, fn, kind, occ):
+    """oracle_sparse_op_rows (arbitrary rows: the reference's startrow loop, sparseop.cpp:186-201) reproduces
+    the rows of the compiled reference's operators -- the entry the full-size sampled-row parity gates use."""
+    _, n, ints = load(fn, kind)
+    tag = f"{fn}.{kind}{occ[0]}{occ[1]}"
+    dets = small[tag + ".dets"]
+    nd = len(dets)
+    rows = np.unique(np.concatenate([[0, nd - 1, nd // 2], np.random.default_rng(5).integers(0, nd, 40)]))[::-1]
+    for name, sym in (("sym", True), ("nonsym", False)):
+        if tag + f".{name}.indptr" not in small:
+            continue
+        rp, rx, rv = small[f"{tag}.{name}.indptr"], small[f"{tag}.{name}.indices"], small[f"{tag}.{name}.data"]
+        ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, symmetric=sym, rows=rows)
+        assert len(ip) == len(rows) + 1
+        for k, r in enumerate(rows):
+            assert np.array_equal(ix[ip[k]:ip[k + 1]], rx[rp[r]:rp[r + 1]])
+            assert np.array_equal(dv[ip[k]:ip[k + 1]], rv[rp[r]:rp[r + 1]])
+    # restricted column range (rectangular operators) and an empty list
+    ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, symmetric=False, ncol=nd // 2, rows=rows)
+    fp, fx, fv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, symmetric=False, ncol=nd // 2)
+    for k, r in enumerate(rows):
+        assert np.array_equal(ix[ip[k]:ip[k + 1]], fx[fp[r]:fp[r + 1]])
+    ip, ix, dv = O.sparse_op(KIND[kind], n, occ[0], occ[1], dets, ints, rows=np.zeros(0, dtype=np.int64))
+    assert ip.tolist() == [0] and len(ix) == 0
+
+
 @pytest.mark.parametrize("fn,kind,occ", SMALL)
 def test_oracle_small_rdms_bit_exact(small, fn, kind, occ):
     _, n, _ = load(fn, kind)
