@@ -264,38 +264,69 @@ def cpu_sample(spec, seconds):
             "spmv_gbs": nnz * 16 / ts / 1e9 if ts > 0 else None}
 
 
-def run_reference(args, spec, rank, world):
-    if rank != 0:
-        return 0
+def _ref_worker(job):
+    """One process of the reference arm: the compiled reference's sparse_op on a k-row slice, `steps` times, started
+    together with its siblings (barrier) so that the processes load the host at the same time."""
+    spec, k, steps, warmup, barrier = job
     cp = CpuPath(spec)
-    k = cp.rows_for(4.0)  # ~4 s of host work per step
-    per_row = ref_size_per_row(spec, cp.ndet)
-    if per_row is None:
-        _, nnz0, _ = cp.build_rows(k)
-        per_row = (nnz0 / k - 1.0) / 2.0 + 1.0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         cp.build_rows(max(64, k // 8))
+    barrier.wait()
     t_total, spmv_t, nnz_total = 0.0, 0.0, 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         t, nnz, ts = cp.build_rows(k)
         t_total += t
         spmv_t += ts
         nnz_total += nnz
-    value = (k * args.steps / t_total) * per_row
+    return t_total, spmv_t, nnz_total, cp.kind, cp.ndet
+
+
+def run_reference(args, spec, rank, world):
+    """The reference's own CPU implementation of the path on the box's host cores.  Its row loop is serial
+    (sparseop.cpp:196-199, no OpenMP in its Makefile), so "all the host threads it can use" is one per process:
+    `cores` processes (one per host core, at most 32) each build a k-row slice through the reference's public
+    sparse_op(ham, wfn, nrow=k, symmetric=False) at the same time; value = summed rows/s x stored nnz per row of the
+    default operator.  The single-process rate is reported beside it."""
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cp = CpuPath(spec)
+    k = cp.rows_for(4.0)  # ~4 s of host work per step and process
+    per_row = ref_size_per_row(spec, cp.ndet)
+    if per_row is None:
+        _, nnz0, _ = cp.build_rows(k)
+        per_row = (nnz0 / k - 1.0) / 2.0 + 1.0
+    t1, _, _ = cp.build_rows(k)
+    single = (k / t1) * per_row
+    ndet, kind = cp.ndet, cp.kind
+    del cp
+    cores = max(1, min(os.cpu_count() or 1, 32, args.ref_procs if args.ref_procs > 0 else 1 << 30))
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        barrier = mgr.Barrier(cores)
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_ref_worker, [(spec, k, args.steps, args.warmup, barrier)] * cores, chunksize=1)
+    rows_per_s = sum(k * args.steps / r[0] for r in res)
+    value = rows_per_s * per_row
+    spmv_t = sum(r[1] for r in res)
+    nnz_total = sum(r[2] for r in res)
     line = {
         "impl": "reference", "metric": "sparse_op_build_nnz_per_s", "value": value, "unit": "nnz/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean([r[0] for r in res])) / args.steps,
         "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic" if "n" in spec else "reference test FCIDUMP",
-        "config": {"workload": spec["label"], "ndet": cp.ndet, "rows_per_step": k},
-        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": cp.kind,
-                         "sample": "each step builds the first %d of %d rows x all columns with the reference's "
-                                   "sparse_op(nrow=k, symmetric=False); rows/s scaled by %.1f stored nnz/row of the "
-                                   "default operator; single-threaded by construction (sparseop.cpp:196-199), host "
-                                   "has %d cores" % (k, cp.ndet, per_row, os.cpu_count() or 1)},
+        "config": {"workload": spec["label"], "ndet": ndet, "rows_per_step": k, "processes": cores},
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": cores, "kind": kind,
+                         "single_core_value": single,
+                         "sample": "%d processes (one per host core, <= 32; the reference's row loop is serial, "
+                                   "sparseop.cpp:196-199) each build the first %d of %d rows x all columns with the "
+                                   "reference's sparse_op(nrow=k, symmetric=False) per step, at the same time; summed "
+                                   "rows/s scaled by %.1f stored nnz/row of the default operator; host has %d cores"
+                                   % (cores, k, ndet, per_row, os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "spmv": {"gbs": nnz_total * 16 / spmv_t / 1e9 if spmv_t > 0 else None, "bytes_per_nnz": 16,
-                 "note": "row-slice CSR product through the same compiled code"},
+                 "note": "row-slice CSR product through the same compiled code, per process"},
         "gpu_launches": 0,
     }
     emit(line)
@@ -306,162 +337,400 @@ def run_reference(args, spec, rank, world):
 # this repo's arm
 
 
-def run_b200(args, spec, rank, world, local):
-    import torch
+class Bench:
+    """Process-wide state of the B200 arm: device context, rank plumbing, measured peak."""
 
-    import pyci_b200 as pyci
-    from pyci_b200 import cabi
-    from pyci_b200.distributed import exchange_unique_id
+    def __init__(self, args, rank, world, local):
+        import torch
 
-    if not torch.cuda.is_available() or pyci.device_count() == 0:
-        raise SystemExit("bench.py: no CUDA device; the pyci_b200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", rank=rank, world_size=world)
+        import pyci_b200 as pyci
+        from pyci_b200 import cabi
+        from pyci_b200.distributed import exchange_unique_id
+        self.torch, self.pyci, self.cabi, self.args = torch, pyci, cabi, args
+        self.rank, self.world, self.local = rank, world, local
+        if not torch.cuda.is_available() or pyci.device_count() == 0:
+            raise SystemExit("bench.py: no CUDA device; the pyci_b200 path has no CPU fallback")
+        torch.cuda.set_device(local)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group(backend="nccl", rank=rank, world_size=world)
+            self.dist = dist
+        # the library launches on torch's current stream so that torch.cuda.Event brackets its kernels
+        self.stream = torch.cuda.Stream(device=local)
+        torch.cuda.set_stream(self.stream)
+        pyci.set_device(local, self.stream.cuda_stream)
+        if world > 1:
+            pyci.init_comm(rank, world, exchange_unique_id(pyci.nccl_unique_id, rank, world))
+        self.ctx = cabi.Context(local, self.stream.cuda_stream)
+        if world > 1:
+            self.ctx.init_comm(rank, world, exchange_unique_id(cabi.nccl_unique_id, rank, world))
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks
+                         else "fallback 6650 GB/s (B200_PROFILING.md)")
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
+    def _reduce(self, x, op):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist else x
 
-    # the library launches on torch's current stream so that torch.cuda.Event brackets its kernels
-    stream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(stream)
-    pyci.set_device(local, stream.cuda_stream)
-    if world > 1:
-        pyci.init_comm(rank, world, exchange_unique_id(pyci.nccl_unique_id, rank, world))
-    ctx = cabi.Context(local, stream.cuda_stream)
-    if world > 1:
-        ctx.init_comm(rank, world, exchange_unique_id(cabi.nccl_unique_id, rank, world))
+    def min(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MIN) if self.dist else x
 
-    # ---- host inputs (numpy arrays / host wave function), built once, untimed
-    note("building host inputs: " + spec["label"])
-    ham, wfn = make_problem(pyci, spec)
-    note("host inputs ready: %d determinants" % len(wfn))
-    ndet = len(wfn)
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def close(self):
+        self.ctx.close()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def device_inputs(B, spec):
+    """(dham, dwfn, kind, host integrals for the checker, h2d bytes of the e2e call) through the C ABI.  Complete
+    spaces are unranked on the device (Wfn::add_all_dets); config 5 uploads its explicit determinant array."""
+    cabi = B.cabi
+    syn = _synthetic()
     kind = {"doci": cabi.DOCI, "fullci": cabi.FULLCI, "genci": cabi.GENCI}[spec["kind"]]
-    dets = wfn.to_det_array()
-    h2d_bytes = dets.nbytes + ham.one_mo.nbytes + ham.two_mo.nbytes + ham.h.nbytes + ham.v.nbytes + ham.w.nbytes
+    if "cfg5" in spec:
+        K, Pn, nd = spec["cfg5"]
+        _, one, two = syn.synthetic_integrals(K, SEED)
+        h_so, g_so = syn.spin_orbital_integrals(one, two)
+        dets = syn.seniority_zero_genci_dets(K, Pn, nd)
+        dham = cabi.Ham(B.ctx, 2 * K, 0.0, h_so, g_so)
+        dwfn = cabi.Wfn(B.ctx, kind, 2 * K, 2 * Pn, 0, dets)
+        return dham, dwfn, kind, dict(n=2 * K, occ=(2 * Pn, 0), ecore=0.0, one=h_so, two=g_so, dets=dets)
+    if "file" in spec:
+        ham = B.pyci.secondquant_op(datafile(spec["file"]))
+        n, ecore, one, two = ham.nbasis, ham.ecore, ham.one_mo, ham.two_mo
+        hvw = (ham.h, ham.v, ham.w)
+    else:
+        ecore, one, two = syn.synthetic_integrals(spec["n"], SEED)
+        n, hvw = spec["n"], (None, None, None)
+    dham = cabi.Ham(B.ctx, n, ecore, one, two, *hvw)
+    dwfn = cabi.Wfn(B.ctx, kind, n, spec["occ"][0], spec["occ"][1])
+    return dham, dwfn, kind, dict(n=n, occ=tuple(spec["occ"]), ecore=ecore, one=one, two=two, hvw=hvw, dets=None)
 
-    # ---- device-resident inputs for the kernel-side number
-    dham = cabi.Ham(ctx, ham.nbasis, ham.ecore, ham.one_mo, ham.two_mo, ham.h, ham.v, ham.w)
-    dwfn = cabi.Wfn(ctx, kind, ham.nbasis, wfn.nocc_up, wfn.nocc_dn, dets)
 
+def gate_rows(row0, nloc, nb, rng, target):
+    """Rows the parity gate compares: first / last rows of the shard, both sides of alpha-string boundaries (every
+    nb rows; the complete-space fill restages there) and of uniform CTA range boundaries (one and four ranges per SM),
+    random rest."""
+    if nloc <= 0:
+        return np.zeros(0, dtype=np.int64)
+    rows = {row0, row0 + 1, row0 + nloc - 1, row0 + nloc - 2}
+    bounds = np.zeros(0, dtype=np.int64)
+    if nb:
+        bounds = np.arange(-(-row0 // nb) * nb, row0 + nloc, nb)
+        if len(bounds) > 40:
+            bounds = np.concatenate([bounds[:10], bounds[-10:], rng.choice(bounds[10:-10], 20, replace=False)])
+    for parts in (148, 592):
+        per = -(-nloc // parts)
+        cb = row0 + per * np.arange(1, parts)
+        cb = cb[cb < row0 + nloc]
+        if len(cb):
+            bounds = np.concatenate([bounds, rng.choice(cb, min(24, len(cb)), replace=False)])
+    for b in bounds:
+        rows.update((int(b) - 1, int(b), int(b) + 1))
+    rows.update(int(r) for r in rng.integers(row0, row0 + nloc, max(0, target - len(rows))))
+    return np.array(sorted(r for r in rows if row0 <= r < row0 + nloc), dtype=np.int64)
+
+
+def parity_gate(B, spec, op, dwfn, kind, host, target):
+    """BASELINE.md 4.4 gate on the TIMED operator of this rank: sampled rows exported from HBM (pyci_op_export_rows)
+    against the CPU oracle's row-list entry (the checker; pinned against the compiled reference by tests/test_oracle.py):
+    indptr / indices bit-equal, data <= 1e-12 relative.  Returns per-rank numbers; reduced by the caller."""
+    from oracle import oracle as O
+    okind = {"doci": O.DOCI, "fullci": O.FULLCI, "genci": O.GENCI}[spec["kind"]]
+    dets = host["dets"] if host["dets"] is not None else dwfn.download_dets()
+    n, occ = host["n"], host["occ"]
+    from math import comb
+    nb = comb(n, occ[1]) if spec["kind"] == "fullci" else 0
+    rng = np.random.default_rng(1000 + B.rank)
+    rows = gate_rows(op.row_begin, op.row_count, nb, rng, target)
+    if spec["kind"] == "doci":
+        ints = O.senzero_integrals(host["one"], host["two"])
+    else:
+        ints = (host["one"], host["two"])
+    t0 = time.perf_counter()
+    gi, gx, gd = op.export_rows(rows)
+    oi, ox, od = O.sparse_op(okind, n, occ[0], occ[1], dets, ints, rows=rows)
+    same = bool(np.array_equal(gi, oi) and np.array_equal(gx, ox))
+    if same and len(od):
+        rel = float(np.max(np.abs(gd - od)) / max(np.max(np.abs(od)), 1e-300))
+        bit = bool(np.array_equal(gd, od))
+    else:
+        rel, bit = (0.0, True) if same else (float("inf"), False)
+    return {"rows": int(len(rows)), "entries": int(len(ox)), "structure_equal": same, "max_rel": rel,
+            "data_bit_identical": bit, "seconds": time.perf_counter() - t0}
+
+
+def reduce_parity(B, g):
+    out = {"rows": int(B.sum(g["rows"])), "entries": int(B.sum(g["entries"])),
+           "structure_equal": bool(B.min(1.0 if g["structure_equal"] else 0.0) > 0.5),
+           "max_rel": B.max(g["max_rel"]) if np.isfinite(g["max_rel"]) else float("inf"),
+           "data_bit_identical": bool(B.min(1.0 if g["data_bit_identical"] else 0.0) > 0.5),
+           "ranks": B.world, "checker_seconds": B.max(g["seconds"]),
+           "against": "oracle_sparse_op_rows (CPU restatement pinned to the compiled reference) on sampled rows of the "
+                      "timed operator: shard ends, alpha-string and CTA-range boundaries, random rest"}
+    out["ok"] = bool(out["structure_equal"] and out["max_rel"] <= 1e-12)
+    return out
+
+
+def golden_e0(spec):
+    """E0 of the oracle-built operator by ARPACK (tests/golden/e0_syn.json, made by tests/golden/make_golden_e0.py),
+    or the energies the reference's own tests pin (pyci/test/test_routines.py:44-45)."""
+    if spec.get("key") == "cfg1":
+        return -14.617409507, 1e-9, "pyci/test/test_routines.py:44 (atol 1e-9)"
+    if spec.get("key") == "cfg2":
+        return -75.634588422, 1e-9, "pyci/test/test_routines.py:45 (atol 1e-9)"
+    if "n" in spec and "cfg5" not in spec:
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "e0_syn.json")) as f:
+                g = json.load(f).get("syn%d" % spec["n"])
+            if g and tuple(g["occ"]) == tuple(spec["occ"]):
+                return g["E0"], 1e-10, "tests/golden/e0_syn.json (oracle-built operator + ARPACK, %d matvecs)" % g["arpack_matvecs"]
+        except (OSError, ValueError):
+            pass
+    return None, None, None
+
+
+def measure_case(B, spec, steps, warmup, gate_target=1000, rdm=False, clocks=False):
+    """One workload through the C ABI with device-resident inputs: timed constructions (CUDA events on the bench
+    stream, max over ranks), the parity gate on the timed operator, SpMV per-launch timing, time to E0, optionally
+    the RDMs.  Returns (result dict, live objects for the caller's extra legs)."""
+    cabi, torch = B.cabi, B.torch
+    note("inputs: " + spec["label"])
+    dham, dwfn, kind, host = device_inputs(B, spec)
+    ndet = dwfn.ndet
     state = {"op": None}
 
     def step_device():
         if state["op"] is not None:
             state["op"].close()
         dwfn.reindex()
-        state["op"] = cabi.Op(ctx, dham, dwfn)
+        state["op"] = cabi.Op(B.ctx, dham, dwfn)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
-    note("warm-up done, timing %d constructions" % args.steps)
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    ctx.reset_launches()
+    note("warm-up done, timing %d constructions" % steps)
+    sampler = ClockSampler(B.local) if clocks else None
+    if sampler:
+        sampler.start()
+    B.barrier()
+    B.ctx.reset_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    per_step = []
-    for _ in range(args.steps):
+    e0.record(B.stream)
+    per_step, fills = [], []
+    for _ in range(steps):
         step_device()
         bt = state["op"].build_times()
         per_step.append(dwfn_index_seconds(cabi, dwfn) + bt["total"])
-    e1.record(stream)
-    barrier()
-    launches = ctx.launches
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        fills.append(state["op"].fill_seconds())
+    e1.record(B.stream)
+    B.barrier()
+    launches = B.ctx.launches
+    dev_ms = B.max(e0.elapsed_time(e1))
     op = state["op"]
-    size_total = sum_over_ranks(op.size)
-    stored_total = sum_over_ranks(op.stored_nnz)
-    value = size_total * args.steps / (dev_ms * 1e-3)
+    size_total = B.sum(op.size)
+    stored_total = B.sum(op.stored_nnz)
     bt = op.build_times()
-    fill_s = max_over_ranks(bt["fill_sort"])
-    kernel_s = max_over_ranks(float(np.mean(per_step)))
+    fill_kernel_s = B.max(float(np.mean(fills)))
+    kernel_s = B.max(float(np.mean(per_step)))
+
+    # ---- parity gate on the operator that was just timed (BASELINE.md 4.4), every rank
+    note("parity gate")
+    parity = reduce_parity(B, parity_gate(B, spec, op, dwfn, kind, host, gate_target))
 
     # ---- SpMV: per-launch CUDA events inside the library, on the same stream
     note("SpMV timing")
-    reps = max(args.steps, 10)
-    ms = op.time_spmv(max(args.warmup, 3), reps, 0)
-    spmv_ms = max_over_ranks(float(np.mean(ms)))
+    reps = max(steps, 10)
+    ms = op.time_spmv(max(warmup, 3), reps, 0)
+    spmv_ms = B.max(float(np.mean(ms)))
     spmv_bytes = op.stored_nnz * 12 + (op.row_count + 1) * 8 + op.row_count * 8 + op.ncol * 8
-    spmv_bytes_total = sum_over_ranks(spmv_bytes)
-    clocks = sampler.summary()
-
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-
+    spmv_bytes_total = B.sum(spmv_bytes)
+    clk = sampler.summary() if sampler else None
     spmv_gbs = spmv_bytes / (spmv_ms * 1e-3) / 1e9  # per GPU
     fill_bytes = op.stored_nnz * 12 + (op.row_count + 1) * 8 + op.row_count * (16 if kind == cabi.FULLCI else 8)
-    fill_gbs = fill_bytes / max(fill_s, 1e-9) / 1e9
-    fill_name = op.fill_kernel()
-    op_rows = op.row_count
-    spmv_name = "spmv_rows" if spmv_bytes / max(op_rows, 1) > 12 * 320 else "spmv_short_rows"
-    traffic = {}
-    try:  # dram bytes per launch from the committed ncu --set full captures (single-GPU workloads only)
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(spec.get("key", "") if world == 1 else "", {})
-    except (OSError, ValueError):
-        pass
+    fill_gbs = fill_bytes / max(fill_kernel_s, 1e-9) / 1e9
+    fill_name, count_name = op.fill_kernel(), op.count_kernel()
+    spmv_name = "spmv_rows" if spmv_bytes / max(op.row_count, 1) > 12 * 320 else "spmv_short_rows"
+    op_bytes = spmv_bytes
 
     # ---- time to E0: one more construction + the Davidson solve, device-timed
     note("time to E0")
-    barrier()
+    B.barrier()
     t0 = time.perf_counter()
     step_device()
     op = state["op"]
     bt2 = op.build_times()
     evals, evecs, st = op.solve(n=1, tol=E_TOL)
     torch.cuda.synchronize()
-    tte_wall = max_over_ranks(time.perf_counter() - t0)
-    tte_dev = max_over_ranks(dwfn_index_seconds(cabi, dwfn) + bt2["total"] + st["seconds"])
+    tte_wall = B.max(time.perf_counter() - t0)
+    tte_dev = B.max(dwfn_index_seconds(cabi, dwfn) + bt2["total"] + st["seconds"])
     op.close()
     state["op"] = None
+    gold, gtol, gsrc = golden_e0(spec)
+    parity["dE0"] = abs(float(evals[0]) - (gold + (host["ecore"] if "n" in spec else 0.0))) if gold is not None else None
+    parity["E0_reference"] = gsrc
+    parity["E0_residual"] = st["residual"]
+    if gold is not None:
+        parity["ok"] = bool(parity["ok"] and parity["dE0"] <= max(gtol, 1e-10))
+
+    out = {
+        "workload": spec["label"], "ndet": int(ndet), "ms_per_step": dev_ms / steps, "dev_ms": dev_ms,
+        "value": size_total * steps / (dev_ms * 1e-3), "nnz_reference_format": int(size_total),
+        "nnz_streamed_full_rows": int(stored_total), "gpu_launches": int(launches), "clocks": clk,
+        "parity": parity,
+        "roofline": {"kernel": fill_name, "bound": "hbm", "achieved": fill_gbs, "peak": B.peak, "unit": "GB/s",
+                     "frac": fill_gbs / B.peak, "traffic": None, "peak_source": B.peak_src,
+                     "bytes_per_launch": int(fill_bytes), "ms_per_launch": 1e3 * fill_kernel_s,
+                     "share_of_step": fill_kernel_s / max(dev_ms * 1e-3 / steps, 1e-12),
+                     "note": "bytes = CSR written once (12 B per stored non-zero + row pointer) + determinants read once; "
+                             "duration = CUDA events around the fill kernel's launch alone, inside the library, on the "
+                             "bench stream (mean of the timed steps, max over ranks)"},
+        "roofline_spmv": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": B.peak, "unit": "GB/s",
+                          "frac": spmv_gbs / B.peak, "traffic": None, "peak_source": B.peak_src,
+                          "bytes_per_launch": int(spmv_bytes), "ms_per_launch": spmv_ms},
+        "spmv": {"gbs_per_gpu": spmv_gbs, "gbs_total": spmv_bytes_total / (spmv_ms * 1e-3) / 1e9, "ms": spmv_ms,
+                 "bytes_per_nnz": 12, "frac_of_peak": spmv_gbs / B.peak},
+        "build": {"kernel_seconds_per_step": kernel_s, "index_s": dwfn_index_seconds(cabi, dwfn),
+                  "count_scan_s": bt["count_scan"], "fill_sort_s": bt["fill_sort"], "fill_kernel_s": fill_kernel_s,
+                  "step_minus_fill_ms": dev_ms / steps - 1e3 * fill_kernel_s, "count_kernel": count_name,
+                  "full_nnz_per_s": stored_total / max(kernel_s, 1e-9)},
+        "time_to_e0": {"seconds_device": tte_dev, "seconds_wall": tte_wall, "E0": float(evals[0]), "matvecs": st["matvecs"],
+                       "residual": st["residual"], "tol": E_TOL, "solve_seconds": st["seconds"],
+                       "spmv_seconds": st["spmv_seconds"]},
+        "operator_bytes_per_gpu": int(op_bytes),
+    }
+    if rdm:
+        note("RDMs")
+        B.barrier()
+        t0 = time.perf_counter()
+        d1, d2 = cabi.compute_rdms(B.ctx, dwfn, kind, host["n"], evecs[0])
+        torch.cuda.synchronize()
+        out["rdm"] = {"seconds_wall": B.max(time.perf_counter() - t0),
+                      "energy_identity_abs_error": abs(rdm_energy_arrays(spec, host, d1, d2) - float(evals[0])),
+                      "call": "pyci_compute_rdms(ctx, wfn, c0): coefficients up, contraction, all-reduce, tensors back"}
+        del d1, d2
+    live = {"dham": dham, "dwfn": dwfn, "kind": kind, "host": host, "evals": evals, "evecs": evecs}
+    return out, live
+
+
+def rdm_energy_arrays(spec, host, d1, d2):
+    """E = ecore + sum h gamma + 1/4 sum <pq||rs> Gamma in the spin-orbital basis (test_routines.py:130-133)."""
+    if spec["kind"] == "genci":
+        h2, g2, r1, r2 = host["one"], host["two"], d1, d2
+    else:
+        import pyci_b200 as pyci
+        h2, g2 = _synthetic().spin_orbital_integrals(host["one"], host["two"])
+        r1, r2 = pyci.spinize_rdms(d1, d2)
+    e2 = np.einsum("ijkl,ijkl", g2, r2) - np.einsum("ijlk,ijkl", g2, r2)
+    return host["ecore"] + np.einsum("ij,ij", h2, r1) + 0.25 * e2
+
+
+def cpu_time_to_e0(B, names):
+    """BASELINE.md 4.3 on the host, beside the same workloads on the GPU: t_build_cpu = the compiled reference's
+    sparse_op(ham, wfn) (1 core: its row loop is serial), t_eigsh = scipy eigsh(k=1, which='SA', tol=1e-12, ncv=30) on
+    the full symmetric matrix with its matvec count; GPU: construction + Davidson through the C ABI."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    ref, kind = load_reference(False)
+    out = []
+    for name in names:
+        spec = workload_spec(name)
+        spec["key"] = name
+        row = {"workload": spec["label"]}
+        res, live = measure_case(B, spec, 2, 1, gate_target=200)
+        row.update(gpu_seconds_to_e0=res["time_to_e0"]["seconds_device"], gpu_matvecs=res["time_to_e0"]["matvecs"],
+                   gpu_E0=res["time_to_e0"]["E0"], gpu_build_ms=res["ms_per_step"], parity=res["parity"])
+        live["dwfn"].close()
+        live["dham"].close()
+        if ref is not None:
+            ham, wfn = make_problem(ref, spec)
+            t0 = time.perf_counter()
+            op = ref.sparse_op(ham, wfn)
+            t1 = time.perf_counter()
+            L = sp.csr_matrix((op.data(), op.indices(), op.indptr()), shape=(len(wfn),) * 2)
+            A = (L + sp.tril(L, -1).T).tocsr()
+            count = [0]
+
+            def mv(x, A=A, count=count):
+                count[0] += 1
+                return A @ x
+
+            t2 = time.perf_counter()
+            w, _ = spla.eigsh(spla.LinearOperator(A.shape, matvec=mv, dtype=np.float64), k=1, which="SA", tol=1e-12,
+                              ncv=min(30, len(wfn) - 1))
+            t3 = time.perf_counter()
+            row.update(cpu_kind=kind, cpu_cores=1, t_build_cpu=t1 - t0, t_eigsh_cpu=t3 - t2,
+                       t_e0_cpu=(t1 - t0) + (t3 - t2), arpack_matvecs=count[0], cpu_E0=float(w[0] + ham.ecore),
+                       dE0_gpu_vs_cpu=abs(float(w[0] + ham.ecore) - row["gpu_E0"]))
+        out.append(row)
+    return out
+
+
+def run_b200(args, spec, rank, world, local):
+    B = Bench(args, rank, world, local)
+    cabi, pyci, torch = B.cabi, B.pyci, B.torch
+    res, live = measure_case(B, spec, args.steps, args.warmup, gate_target=args.gate_rows, rdm=False, clocks=True)
+    ndet = res["ndet"]
+    traffic = {}
+    try:  # dram bytes per launch from the committed ncu --set full captures (single-GPU workloads only)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(spec.get("key", "") if world == 1 else "", {})
+    except (OSError, ValueError):
+        pass
+    res["roofline"]["traffic"] = traffic.get(res["roofline"]["kernel"], {}).get("bytes")
+    res["roofline_spmv"]["traffic"] = traffic.get(res["roofline_spmv"]["kernel"], {}).get("bytes")
+    live["dwfn"].close()
+    live["dham"].close()
+    evals, evecs = live["evals"], live["evecs"]
+
+    # ---- host objects for the public-API legs (built once, untimed)
+    note("building host inputs: " + spec["label"])
+    ham, wfn = make_problem(pyci, spec)
+    full_space = "cfg5" not in spec
+    h2d_bytes = ham.one_mo.nbytes + ham.two_mo.nbytes + ham.h.nbytes + ham.v.nbytes + ham.w.nbytes
+    if not full_space:
+        h2d_bytes += wfn.to_det_array().nbytes
 
     # ---- 1- and 2-RDM of the ground state through the public API (collective when row-sharded), checked by
     # the energy identity of the reference's test_compute_rdms (test_routines.py:115-133)
     note("RDMs")
-    barrier()
+    B.barrier()
     t0 = time.perf_counter()
     d1, d2 = pyci.compute_rdms(wfn, evecs[0])
     torch.cuda.synchronize()
-    rdm_wall = max_over_ranks(time.perf_counter() - t0)
+    rdm_wall = B.max(time.perf_counter() - t0)
     rdm_err = abs(rdm_energy(pyci, ham, spec, wfn, d1, d2) - float(evals[0])) if rank == 0 else 0.0
     del evecs, d1, d2
 
     # ---- selected CI on a thinned FullCI space: one heat-bath iteration (add_hci) and the ENPT2 energy, device
     # seconds of the walk + merge; the reference's own routines timed beside them on a row sample (rank 0)
-    barrier()
+    B.barrier()
     note("selected-CI leg")
-    sel = selected_ci_leg(cabi, ctx, rank, world, not args.no_cpu_baseline, spec["kind"] == "genci")
+    sel = selected_ci_leg(cabi, B.ctx, rank, world, not args.no_cpu_baseline, spec["kind"] == "genci")
 
-    # ---- end to end through the public API, host buffers in, row pointer out
+    # ---- end to end through the public API, host objects in, row pointer out
     d2h_bytes = 0
-
     split = [0.0, 0.0]
 
     def step_e2e():
@@ -474,70 +743,85 @@ def run_b200(args, spec, rank, world, local):
         split[0] += tb - ta
         split[1] += tc - tb
         d2h_bytes = ip.nbytes
-        return o.size, int(ip[-1])
+        return o, int(ip[-1])
 
     note("end-to-end leg")
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
-    barrier()
+    B.barrier()
     split[0] = split[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sz, _ = step_e2e()
+        o, sz = step_e2e()
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = sum_over_ranks(sz) * args.steps / e2e_s
+    e2e_s = B.max(time.perf_counter() - t0)
+    e2e_value = B.sum(sz) * args.steps / e2e_s
+    del o
 
     line = {
-        "metric": "sparse_op_build_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "metric": "sparse_op_build_nnz_per_s", "value": res["value"], "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic" if "n" in spec else "reference test FCIDUMP",
-        "config": {"workload": spec["label"], "ndet": ndet, "nnz_reference_format": int(size_total),
-                   "nnz_streamed_full_rows": int(stored_total), "parallelism": "row-shard x%d" % world,
+        "config": {"workload": spec["label"], "ndet": ndet, "nnz_reference_format": res["nnz_reference_format"],
+                   "nnz_streamed_full_rows": res["nnz_streamed_full_rows"], "parallelism": "row-shard x%d" % world,
                    "l2": "operator (%.1f GB/GPU) is larger than the 126 MB L2: no flush between iterations"
-                         % (spmv_bytes / 1e9) if spmv_bytes > 4 * 126e6 else "operator fits L2: numbers are L2-resident"},
+                         % (res["operator_bytes_per_gpu"] / 1e9) if res["operator_bytes_per_gpu"] > 4 * 126e6
+                         else "operator fits L2: numbers are L2-resident"},
         "e2e": {"value": e2e_value, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "ms_sparse_op": 1e3 * split[0] / args.steps, "ms_indptr": 1e3 * split[1] / args.steps,
-                "call": "pyci_b200.sparse_op(ham, wfn); op.indptr()  (host arrays in, pageable)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+                "call": "pyci_b200.sparse_op(ham, wfn); op.indptr()  (host objects in, pageable; a wave function filled "
+                        "by add_all_dets is defined by (nbasis, nocc_up, nocc_dn) and is unranked on the device, so the "
+                        "bytes that cross PCIe are the integrals in and the row pointer out)" if full_space else
+                        "pyci_b200.sparse_op(ham, wfn); op.indptr()  (host arrays in, pageable)"},
+        "gpu_launches": res["gpu_launches"],
+        "clocks": res["clocks"],
+        "parity": res["parity"],
         # the dominant kernel of the timed step (one construction) is the fill kernel; the SpMV kernel that the
         # solve spends its time in is reported beside it
-        "roofline": {"kernel": fill_name, "bound": "hbm", "achieved": fill_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": fill_gbs / peak, "traffic": traffic.get(fill_name, {}).get("bytes"), "peak_source": peak_src,
-                     "bytes_per_launch": int(fill_bytes), "ms_per_launch": 1e3 * fill_s,
-                     "share_of_step": fill_s / max(dev_ms * 1e-3 / args.steps, 1e-12),
-                     "note": "bytes = CSR written once (12 B per stored non-zero + row pointer) + determinants read once; "
-                             "CUDA events around the kernel launches inside the library, on the bench stream"},
-        "roofline_spmv": {"kernel": spmv_name, "bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
-                          "frac": spmv_gbs / peak, "traffic": traffic.get(spmv_name, {}).get("bytes"), "peak_source": peak_src,
-                          "bytes_per_launch": int(spmv_bytes), "ms_per_launch": spmv_ms},
-        "spmv": {"gbs_per_gpu": spmv_gbs, "gbs_total": spmv_bytes_total / (spmv_ms * 1e-3) / 1e9, "ms": spmv_ms,
-                 "bytes_per_nnz": 12, "frac_of_peak": spmv_gbs / peak},
-        "build": {"kernel_seconds_per_step": kernel_s, "index_s": dwfn_index_seconds(cabi, dwfn),
-                  "count_scan_s": bt["count_scan"], "fill_sort_s": bt["fill_sort"],
-                  "full_nnz_per_s": stored_total / max(kernel_s, 1e-9)},
-        "time_to_e0": {"seconds_device": tte_dev, "seconds_wall": tte_wall, "E0": float(evals[0]), "matvecs": st["matvecs"],
-                       "residual": st["residual"], "tol": E_TOL, "solve_seconds": st["seconds"],
-                       "spmv_seconds": st["spmv_seconds"]},
+        "roofline": res["roofline"], "roofline_spmv": res["roofline_spmv"], "spmv": res["spmv"], "build": res["build"],
+        "time_to_e0": res["time_to_e0"],
         "rdm": {"seconds_wall": rdm_wall, "energy_identity_abs_error": rdm_err,
                 "call": "pyci_b200.compute_rdms(wfn, c0): wfn upload + index + contraction + tensors back"},
         "selected_ci": sel,
     }
+    # ---- N = 1: the multi-GPU workload on one GPU (the base of a true strong-scaling curve) and the CPU
+    # time-to-E0 legs; N = 8: BASELINE config 5 at full size
+    if world == 1 and spec.get("key") == "cfg3" and not args.no_extras:
+        free, _ = torch.cuda.mem_get_info(local)
+        if free > 150e9:
+            note("scaling base: config 4 on one GPU")
+            s4 = workload_spec("cfg4")
+            s4["key"] = "cfg4"
+            r4, l4 = measure_case(B, s4, max(2, args.steps // 4), 1, gate_target=args.gate_rows)
+            l4["dwfn"].close()
+            l4["dham"].close()
+            line["scaling_base"] = {k: r4[k] for k in ("workload", "ndet", "ms_per_step", "value", "nnz_reference_format",
+                                                        "parity", "roofline", "spmv", "build", "time_to_e0")}
+        if rank == 0 and not args.no_cpu_baseline:
+            note("CPU time-to-E0 legs")
+            line["cpu_time_to_e0"] = cpu_time_to_e0(B, ["cfg1", "cfg2", "syn10"])
+    if world == 8 and spec.get("key") == "cfg4" and not args.no_extras:
+        note("config 5")
+        s5 = workload_spec("cfg5")
+        s5["key"] = "cfg5"
+        r5, l5 = measure_case(B, s5, 1, 1, gate_target=max(200, args.gate_rows // 4), rdm=True)
+        l5["dwfn"].close()
+        l5["dham"].close()
+        line["cfg5"] = {k: r5[k] for k in ("workload", "ndet", "ms_per_step", "value", "nnz_reference_format",
+                                            "nnz_streamed_full_rows", "parity", "roofline", "roofline_spmv", "spmv", "build",
+                                            "time_to_e0", "rdm")}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         note("CPU baseline (reference, host cores)")
         line["cpu_baseline"] = cpu_sample(spec, args.cpu_seconds)
     note("done")
     if rank == 0:
         emit(line)
-    dwfn.close()
-    dham.close()
-    ctx.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    B.close()
+    if not line["parity"]["ok"]:
+        note("PARITY GATE FAILED: the timed operator differs from the oracle; the numbers above are not valid")
+        return 1
     return 0
 
 
@@ -663,6 +947,10 @@ def main():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-procs", type=int, default=0, help="processes of the reference arm (0 = one per core, <= 32)")
+    ap.add_argument("--gate-rows", type=int, default=1000, help="rows per rank compared with the oracle (parity gate)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs (config 4 on one GPU and the CPU time-to-E0 legs at N=1, config 5 at N=8)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))

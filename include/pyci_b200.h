@@ -88,6 +88,10 @@ PYCI_API void pyci_ham_destroy(pyci_ham *ham);
  * determinants return PYCI_ERR_VALUE. */
 PYCI_API int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
                     const uint64_t *dets, pyci_wfn **out);
+/* Wfn::add_all_dets (onespinwfn.cpp:173-217, twospinwfn.cpp:181-245): the complete space of (nbasis, nocc_up,
+ * nocc_dn), unranked in HBM in the reference's order -- colex for DOCI / GenCI, colex(alpha) * C(nbasis, nocc_dn) +
+ * colex(beta) for FullCI -- so that a wave function filled by add_all_dets needs no determinant upload. */
+PYCI_API int pyci_wfn_create_all_dets(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, pyci_wfn **out);
 PYCI_API void pyci_wfn_destroy(pyci_wfn *wfn);
 /* Rebuild the hash index from the determinants already resident in HBM (what SparseOp::update's
  * callers get from Wfn::add_det, onespinwfn.cpp:141-149: the index is part of the construction path).
@@ -161,6 +165,10 @@ PYCI_API double pyci_op_fill_seconds(const pyci_op *op);
 /* name of the CUDA kernel that filled this operator (the dominant kernel of a construction; profiling aid --
  * the reference has one code path, SparseOp::add_row, sparseop.cpp:220-502) */
 PYCI_API const char *pyci_op_fill_kernel(const pyci_op *op);
+/* what found the stored entries of the rows: "analytic" (complete space: the count is a formula), "count_kernel"
+ * (one index probe per candidate excitation, the reference's algorithm) or "join_rows_kernel" (selected spaces:
+ * determinants bucketed by segment pairs and compared by XOR / popcount, join.cuh) */
+PYCI_API const char *pyci_op_count_kernel(const pyci_op *op);
 
 /* py_indptr / py_indices / py_data (sparseop.cpp:504-514) for this rank's rows, in the reference's
  * layout: indptr[row_count+1] starting at 0, indices int64, data fp64, each row sorted by column

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "pyci_ham_upload": (_i, [_vp, _l, _d, _vp, _vp, _vp, _vp, _vp, _vpp]),
     "pyci_ham_destroy": (None, [_vp]),
     "pyci_wfn_upload": (_i, [_vp, _i, _l, _l, _l, _l, _vp, _vpp]),
+    "pyci_wfn_create_all_dets": (_i, [_vp, _i, _l, _l, _l, _vpp]),
     "pyci_wfn_destroy": (None, [_vp]),
     "pyci_wfn_reindex": (_i, [_vp]),
     "pyci_wfn_index_seconds": (_d, [_vp]),
@@ -67,6 +68,7 @@ PROTOTYPES = {
     "pyci_op_build_times": (_i, [_vp, _vp]),
     "pyci_op_fill_seconds": (_d, [_vp]),
     "pyci_op_fill_kernel": (ctypes.c_char_p, [_vp]),
+    "pyci_op_count_kernel": (ctypes.c_char_p, [_vp]),
     "pyci_op_export_csr": (_i, [_vp, _vp, _vp, _vp]),
     "pyci_op_export_rows": (_i, [_vp, _l, _vp, _l, _vp, _vp, _vp]),
     "pyci_op_matvec": (_i, [_vp, _vp, _vp]),
@@ -169,12 +171,18 @@ class Ham:
 class Wfn:
     """pyci_wfn: determinant array + hash index resident in HBM."""
 
-    def __init__(self, ctx, kind, nbasis, nocc_up, nocc_dn, dets):
+    def __init__(self, ctx, kind, nbasis, nocc_up, nocc_dn, dets=None):
+        """dets=None: the complete space, generated on the device (Wfn::add_all_dets)."""
+        self.ctx = ctx
+        self.handle = ctypes.c_void_p()
+        if dets is None:
+            check(lib().pyci_wfn_create_all_dets(ctx.handle, kind, nbasis, nocc_up, nocc_dn, ctypes.byref(self.handle)))
+            self.ndet = int(lib().pyci_wfn_ndet(self.handle))
+            self.det_shape = (2, 1) if kind == FULLCI else (1,)
+            return
         dets = np.ascontiguousarray(dets, dtype=np.uint64)
         self.ndet = int(dets.shape[0])
         self.det_shape = tuple(dets.shape[1:])
-        self.ctx = ctx
-        self.handle = ctypes.c_void_p()
         check(lib().pyci_wfn_upload(ctx.handle, kind, nbasis, nocc_up, nocc_dn, self.ndet, _ptr(dets),
                                     ctypes.byref(self.handle)))
 
@@ -262,6 +270,9 @@ class Op:
 
     def fill_kernel(self):
         return lib().pyci_op_fill_kernel(self.handle).decode()
+
+    def count_kernel(self):
+        return lib().pyci_op_count_kernel(self.handle).decode()
 
     def fill_seconds(self):
         return lib().pyci_op_fill_seconds(self.handle)

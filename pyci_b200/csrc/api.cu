@@ -271,11 +271,7 @@ void pyci_ham_destroy(pyci_ham *ham) {
 
 // ---- wave function -----------------------------------------------------------------------------
 
-int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
-                    const uint64_t *dets, pyci_wfn **out) {
-    if (!ctx || !out || (ndet > 0 && !dets))
-        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
-    *out = nullptr;
+static int wfn_check_args(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn) {
     if (kind != PYCI_DOCI && kind != PYCI_FULLCI && kind != PYCI_GENCI)
         PYCI_FAIL(PYCI_ERR_VALUE, "unknown wave-function kind %d", kind);
     // Wfn::init checks (wfn.cpp:52-57) and the per-class ones (dociwfn.cpp:28, genciwfn.cpp:50)
@@ -292,12 +288,10 @@ int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long noc
     if (nbasis > 64)
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
                   "nbasis = %ld needs multi-word determinants; the device kernels handle nbasis <= 64", nbasis);
-    if (ndet < 0 || ndet >= (1L << 31) - 1)
-        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
-    PYCI_TRY(ctx_activate(ctx));
-    const int nwords = (kind == PYCI_FULLCI) ? 2 : 1;
-    // that every string holds the declared number of electrons inside nbasis orbitals is checked on the device,
-    // together with uniqueness, by the verify pass of the index build
+    return ctx_activate(ctx);
+}
+
+static pyci_wfn *wfn_new(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet) {
     pyci_wfn *wfn = new pyci_wfn();
     wfn->ctx = ctx;
     wfn->kind = kind;
@@ -305,15 +299,57 @@ int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long noc
     wfn->nocc_up = nocc_up;
     wfn->nocc_dn = nocc_dn;
     wfn->ndet = ndet;
-    wfn->nwords = nwords;
+    wfn->nwords = (kind == PYCI_FULLCI) ? 2 : 1;
     if (kind == PYCI_FULLCI)
         wfn->keymode = (nbasis <= 16) ? KEY32 : (nbasis <= 32) ? KEY64 : KEY128;
     else
         wfn->keymode = (nbasis <= 32) ? KEY32 : KEY64;
     wfn->complete = (ndet == full_space_size(kind, nbasis, nocc_up, nocc_dn)); // uniqueness: verified by the index build
-    int rc = upload(&wfn->dets, (const u64 *)dets, (size_t)ndet * nwords, ctx->stream);
+    return wfn;
+}
+
+int pyci_wfn_upload(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, long ndet,
+                    const uint64_t *dets, pyci_wfn **out) {
+    if (!ctx || !out || (ndet > 0 && !dets))
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *out = nullptr;
+    PYCI_TRY(wfn_check_args(ctx, kind, nbasis, nocc_up, nocc_dn));
+    if (ndet < 0 || ndet >= (1L << 31) - 1)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
+    // that every string holds the declared number of electrons inside nbasis orbitals is checked on the device,
+    // together with uniqueness, by the verify pass of the index build
+    pyci_wfn *wfn = wfn_new(ctx, kind, nbasis, nocc_up, nocc_dn, ndet);
+    int rc = upload(&wfn->dets, (const u64 *)dets, (size_t)ndet * wfn->nwords, ctx->stream);
     if (rc == PYCI_OK)
         rc = wfn_build_index(wfn);
+    if (rc != PYCI_OK) {
+        pyci_wfn_destroy(wfn);
+        return rc;
+    }
+    *out = wfn;
+    return PYCI_OK;
+}
+
+int pyci_wfn_create_all_dets(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, long nocc_dn, pyci_wfn **out) {
+    if (!ctx || !out)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *out = nullptr;
+    PYCI_TRY(wfn_check_args(ctx, kind, nbasis, nocc_up, nocc_dn));
+    const long ndet = full_space_size(kind, nbasis, nocc_up, nocc_dn);
+    if (ndet >= (1L << 31) - 1)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
+    pyci_wfn *wfn = wfn_new(ctx, kind, nbasis, nocc_up, nocc_dn, ndet);
+    int rc = wfn_generate_all_dets(wfn, binom_l(nbasis, nocc_up), kind == PYCI_FULLCI ? binom_l(nbasis, nocc_dn) : 1);
+    if (rc == PYCI_OK) {
+        if (kind == PYCI_FULLCI && !getenv("PYCI_B200_EAGER_INDEX")) {
+            // add_all_dets order and valid occupations by construction: nothing to check, the hash index is deferred
+            wfn->sorted2 = true;
+            wfn->index_valid = false;
+            wfn->hash_seconds = 0.0;
+        } else {
+            rc = wfn_build_index(wfn);
+        }
+    }
     if (rc != PYCI_OK) {
         pyci_wfn_destroy(wfn);
         return rc;
@@ -534,6 +570,7 @@ long pyci_op_stored_nnz(const pyci_op *op) { return op->nnz; }
 double pyci_op_ecore(const pyci_op *op) { return op->ecore; }
 
 const char *pyci_op_fill_kernel(const pyci_op *op) { return op ? op->fill_kernel : "none"; }
+const char *pyci_op_count_kernel(const pyci_op *op) { return op ? op->count_kernel : "none"; }
 
 int pyci_op_build_times(const pyci_op *op, double *seconds4) {
     for (int i = 0; i < 4; ++i)

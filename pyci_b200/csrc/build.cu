@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "elements.cuh"
+#include "join.cuh"
 
 namespace {
 
@@ -733,6 +734,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
         ctx->launches++;
         nnz = nloc * ((long)P.ncand + 1);
         maxrow = nloc > 0 ? (int)P.ncand + 1 : 0;
+        op->count_kernel = "analytic";
         PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
     } else {
         if (nloc > 0) {
@@ -754,14 +756,34 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 cudaMemGetInfo(&free_b, &total_b);
                 const long budget = (long)(free_b / 4);
                 long c = std::min<long>(1024, std::min<long>((long)P.ncand, budget / (8 * std::max<long>(nloc, 1))));
-                if (!sorted_path && P.ncand >= 2048 && c >= 32 && !getenv("PYCI_B200_NO_HITLIST")) {
+                const bool force_join = getenv("PYCI_B200_FORCE_JOIN") != nullptr;
+                if (!sorted_path && (P.ncand >= 2048 || force_join) && c >= std::min<long>(32, (long)P.ncand) && c > 0 &&
+                    !getenv("PYCI_B200_NO_HITLIST")) {
                     hitcap = (int)c;
                     PYCI_CUDA(dev_malloc(&hitlist, sizeof(uint2) * (size_t)nloc * (size_t)hitcap));
                 }
             }
-            count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb, hitlist, hitcap,
-                                                                    (u32)((pair_bytes + 7) & ~(size_t)7));
-            ctx->launches++;
+            // Selected two-body space: find the stored entries by joining the determinant list with itself on
+            // segment pairs (join.cuh) when that is predicted to take fewer bit tests than the enumeration takes
+            // probes (a probe costs ~10 tests); else enumerate and probe.
+            bool joined = false;
+            if constexpr (KIND != PYCI_DOCI) {
+                if (hitlist && !getenv("PYCI_B200_NO_JOIN")) {
+                    int used = 0;
+                    const double budget = getenv("PYCI_B200_FORCE_JOIN") ? 1.0e300 : 10.0 * (double)P.ncand * (double)nloc;
+                    PYCI_TRY((join_run<KIND, JOIN_HITLIST>(ctx, wfn, P, hitlist, hitcap, rowcnt, budget, &used, &op->join_tests)));
+                    joined = used != 0;
+                    op->joined = joined;
+                    if (joined)
+                        op->count_kernel = "join_rows_kernel";
+                }
+            }
+            if (!joined) {
+                op->count_kernel = "count_kernel";
+                count_kernel<KIND, KM><<<(unsigned)grid, block, csmem, st>>>(P, ix, nSa, nSb, hitlist, hitcap,
+                                                                        (u32)((pair_bytes + 7) & ~(size_t)7));
+                ctx->launches++;
+            }
         }
         // scan
         const long nb = (nloc + SCAN_BLOCK - 1) / SCAN_BLOCK;

@@ -106,8 +106,11 @@ struct pyci_op {
     int *lowcnt = nullptr;   // [nloc] entries with col <= row (sorted rows => a prefix)
     double *diag = nullptr;  // [npad] diagonal H_ii of this rank's rows (0 where absent)
     double times[4] = {0, 0, 0, 0};
+    bool joined = false;       // selected space: entries found by the segment-pair join (join.cuh), not by enumeration
+    double join_tests = 0.0;   // predicted XOR/popcount tests of that join for this rank's rows
     double fill_seconds = 0.0; // device seconds of the fill kernel alone (CUDA events around its launch)
     const char *fill_kernel = "none"; // which fill path built this operator
+    const char *count_kernel = "none"; // what found the stored entries: "analytic", "count_kernel", "join_rows_kernel"
     int spmv_tpr = 0, spmv_ctas = 4; // SpMV launch shape (threads per row, CTAs per SM), chosen at first use;
                                      // spmv_tpr < 0: bulk-copy stream kernel with -spmv_tpr warps per CTA, ring depth spmv_ctas
     int spmv_depth = 2;              // trips of stream loads in flight per thread in spmv_rows (2, 3 or 4)
@@ -139,6 +142,8 @@ int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, 
 int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count);
 int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
 
+// dets.cu
+int wfn_generate_all_dets(pyci_wfn *wfn, long na, long nb);
 // build.cu
 int wfn_build_index(pyci_wfn *wfn);
 int wfn_ensure_index(const pyci_wfn *wfn); // builds the hash index if it was deferred

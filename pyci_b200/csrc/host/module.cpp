@@ -125,7 +125,7 @@ PYBIND11_MODULE(_pyci, m) {
     py::class_<SparseOp> op(m, "sparse_op", "Sparse matrix operator class (CSR resident in GPU memory).");
     op.def_readonly("ecore", &SparseOp::ecore);
     op.def_readonly("symmetric", &SparseOp::symmetric);
-    op.def_readonly("size", &SparseOp::size);
+    op.def_property_readonly("size", &SparseOp::size);
     op.def_readonly("shape", &SparseOp::shape);
     op.def_property_readonly("dtype", &SparseOp::dtype);
     op.def(py::init([](const SQuantOp &h, const DOCIWfn &w, long r, long c, bool s) { return new SparseOp(h, w, r, c, s); }),

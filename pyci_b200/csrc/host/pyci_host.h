@@ -105,6 +105,9 @@ struct Wfn {
     long nw = 1;   // words per determinant = nspin * nword
     std::vector<ulong> dets;
     DetTable dict;
+    // true while the contents are exactly what add_all_dets produced (nothing added since): such a wave function is
+    // defined by (nbasis, nocc_up, nocc_dn), and the device unranks its determinants itself instead of receiving them
+    bool full_space = false;
 
     virtual ~Wfn() = default;
     virtual int kind() const = 0;
@@ -183,7 +186,7 @@ struct GenCIWfn final : OneSpinWfn {
 
 // ---- SparseOp -----------------------------------------------------------------------------------------
 struct SparseOp {
-    long nrow = 0, ncol = 0, size = 0;
+    long nrow = 0, ncol = 0;
     double ecore = 0.0;
     bool symmetric = true;
     py::tuple shape;
@@ -198,6 +201,7 @@ struct SparseOp {
     void build(const SQuantOp &ham, const Wfn &wfn, long rows, long cols);
     void update(const SQuantOp &ham, const Wfn &wfn);
     py::object dtype() const { return py::dtype::of<double>(); }
+    long size() const { return handle ? pyci_op_size(handle) : 0; } // SparseOp::size, summed on the device at first use
     double get_element(long i, long j) const;
     Array<double> py_matvec(const Array<double> x) const;
     Array<double> py_matvec_out(const Array<double> x, Array<double> y) const;

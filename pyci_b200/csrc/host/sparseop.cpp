@@ -27,6 +27,11 @@ struct DeviceWfn {
     DeviceWfn(const Wfn &wfn) {
         if (wfn.dict.size() != wfn.ndet)
             throw std::invalid_argument("wave function contains duplicate determinants");
+        if (wfn.full_space && !std::getenv("PYCI_B200_UPLOAD_DETS")) {
+            // the contents are add_all_dets' output: the device generates them (no determinant crosses PCIe)
+            check(pyci_wfn_create_all_dets(device_context(), wfn.kind(), wfn.nbasis, wfn.nocc_up, wfn.nocc_dn, &w));
+            return;
+        }
         check(pyci_wfn_upload(device_context(), wfn.kind(), wfn.nbasis, wfn.nocc_up, wfn.nocc_dn, wfn.ndet,
                               reinterpret_cast<const uint64_t *>(wfn.dets.data()), &w));
     }
@@ -95,7 +100,6 @@ void SparseOp::build(const SQuantOp &ham, const Wfn &wfn, long rows, long cols) 
     nrow = rows;
     ncol = cols;
     ecore = ham.ecore;
-    size = pyci_op_size(handle);
     shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
 }
 
@@ -115,8 +119,7 @@ void SparseOp::update(const SQuantOp &ham, const Wfn &wfn) {
         if (rc == PYCI_OK) {
             nrow = ncol = wfn.ndet;
             ecore = ham.ecore;
-            size = pyci_op_size(handle);
-            shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
+                    shape = py::make_tuple(py::cast(nrow), py::cast(ncol));
             return;
         }
         if (rc != PYCI_ERR_UNSUPPORTED)

@@ -34,6 +34,7 @@ void Wfn::init(long nb, long nu, long nd, int nspin_) {
     nw = nword * nspin;
     dets.clear();
     dict.reset(nw);
+    full_space = false;
 }
 
 // binary format: 4 x int64 header (ndet, nbasis, nocc_up, nocc_dn) + raw uint64 determinants
@@ -66,6 +67,7 @@ void Wfn::to_file(const std::string &filename) const {
 // constructor from a determinant array: every row is kept, the dictionary maps a repeated string to
 // its last position (onespinwfn.cpp:55-63, twospinwfn.cpp:55-63)
 void Wfn::set_dets(long n, const ulong *ptr) {
+    full_space = false;
     ndet = n;
     dets.assign(ptr, ptr + n * nw);
     dict.reset(nw);
@@ -103,6 +105,7 @@ long Wfn::add_det(const ulong *det) {
     std::vector<ulong> tmp(det, det + nw);
     dets.insert(dets.end(), tmp.begin(), tmp.end());
     dict.assign(dets, &dets[ndet * nw], ndet);
+    full_space = false;
     return ndet++;
 }
 
@@ -113,6 +116,7 @@ void Wfn::append_new_dets(const ulong *ptr, long n) {
         return;
     dets.insert(dets.end(), ptr, ptr + (size_t)(n * nw));
     dict.insert_new_bulk(dets, ndet, n);
+    full_space = false;
     ndet += n;
 }
 
@@ -161,6 +165,7 @@ void Wfn::add_all_dets(long /*nthread*/) {
     colex_strings(nbasis, nocc_up, nword, maxrank_up, up);
     if (nspin == 1) {
         set_new_dets(maxrank_up, up.data());
+        full_space = nword == 1;
         return;
     }
     colex_strings(nbasis, nocc_dn, nword, maxrank_dn, dn);
@@ -175,6 +180,7 @@ void Wfn::add_all_dets(long /*nthread*/) {
             std::memcpy(d + nword, &dn[b * nword], sizeof(ulong) * nword);
         }
     set_new_dets(n, all.data());
+    full_space = nword == 1;
 }
 
 // replace the contents by n determinants that are distinct by construction (add_all_dets): no key comparisons

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "enumerate.cuh"
+#include "join.cuh"
 
 namespace {
 
@@ -187,17 +188,32 @@ __global__ void __launch_bounds__(256) rdm_kernel(BuildParams P, DetIndex<KM> in
 
 template<int KIND, int KM>
 int run_rdm(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P) {
-    const DetIndex<KM> ix = make_index<KM>(wfn);
+    DetIndex<KM> ix = make_index<KM>(wfn);
     const size_t pb = (pair_table_bytes(P) + 7) & ~(size_t)7;
     const size_t smem = pb + pair_mask_bytes(P, KIND);
-    const long work = (long)P.ncand / 4;
+    BuildParams Pk = P;
+    // Selected two-body space: the connected pairs come from the segment-pair join (join.cuh) instead of one index
+    // probe per candidate excitation; the enumeration kernel then only adds the diagonal terms.
+    if constexpr (KIND != PYCI_DOCI) {
+        const bool force = getenv("PYCI_B200_FORCE_JOIN") != nullptr;
+        if (!wfn->complete && (P.ncand >= 2048 || force) && !getenv("PYCI_B200_NO_JOIN")) {
+            int used = 0;
+            const double budget = force ? 1.0e300 : 10.0 * (double)P.ncand * (double)P.nloc;
+            PYCI_TRY((join_run<KIND, JOIN_RDM>(ctx, wfn, P, nullptr, 0, nullptr, budget, &used, nullptr)));
+            if (used) {
+                Pk.ncand = 0;       // no off-diagonal enumeration
+                ix.bloom = nullptr; // ... and no per-row pair masks for it
+            }
+        }
+    }
+    const long work = (long)Pk.ncand / 4;
     const int block = work <= 256 ? 32 : work <= 1024 ? 64 : work <= 4096 ? 128 : 256;
     int per_sm = 1;
     PYCI_CUDA(cudaFuncSetAttribute(rdm_kernel<KIND, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rdm_kernel<KIND, KM>, block, smem));
     const long grid = std::min<long>(P.nloc, (long)ctx->sm_count * std::max(per_sm, 1));
     if (grid > 0) {
-        rdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(P, ix, (u32)pb);
+        rdm_kernel<KIND, KM><<<(unsigned)grid, block, smem, ctx->stream>>>(Pk, ix, (u32)pb);
         ctx->launches++;
     }
     PYCI_CUDA(cudaGetLastError());
