@@ -13,6 +13,7 @@
 //             streamed to HBM with coalesced stores.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "elements.cuh"
@@ -629,6 +630,7 @@ void free_string_tables(StringTables &T) {
 }
 
 int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, size_t pair_bytes, int *used) {
+    PYCI_NVTX("pyci:fill(complete: string tables + fill_complete_kernel)");
     cudaStream_t st = ctx->stream;
     *used = 0;
     const u32 Na = (u32)binom_d(P.n, P.nocc_a), Nb = S.Nb;
@@ -719,6 +721,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     auto pick_block = [](long work) { return work <= 128 ? 32 : work <= 512 ? 64 : work <= 1024 ? 128 : 256; };
 
     PYCI_CUDA(cudaEventRecord(ctx->ev[0], st));
+    auto *count_range = new PyciRange("pyci:count+scan");
+    std::unique_ptr<PyciRange> count_guard(count_range);
     uint2 *hitlist = nullptr; // (candidate, column) of the hits found by the count pass, [nloc][hitcap]
     int hitcap = 0;
     int *rowcnt = nullptr;
@@ -808,6 +812,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     }
     dev_free(rowcnt);
     P.rowcnt = nullptr;
+    count_guard.reset();
+    PYCI_NVTX("pyci:fill");
 
     op->nnz = nnz;
     PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)(nnz + 4))); // +4: 16-byte bulk reads may overrun the end
@@ -1024,6 +1030,7 @@ int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt
 // The hash index itself (slots + Bloom filter): insert, verify.
 static int wfn_build_hash(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
+    PYCI_NVTX("pyci:index(hash insert+verify)");
     // capacity: power of two with load factor in (0.25, 0.5]
     u64 cap = 16;
     while (cap < 2 * (u64)wfn->ndet)
@@ -1096,6 +1103,7 @@ int wfn_ensure_index(const pyci_wfn *wfn) {
 // fill paths).  Every other wave function gets its hash index here (insert + verify: duplicates, occupations).
 int wfn_build_index(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
+    PYCI_NVTX("pyci:index(check)");
     dev_free(wfn->slots);
     wfn->slots = nullptr;
     wfn->index_valid = false;

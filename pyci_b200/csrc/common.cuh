@@ -12,6 +12,19 @@
 
 #include "../../include/pyci_b200.h"
 
+// NVTX ranges around the phases of the path (index / count / scan / fill / SpMV / all-gather / solve / RDM / HCI):
+// header-only NVTX v3, a no-op unless a profiler (nsys, ncu --nvtx) injects its library.
+#include <nvtx3/nvToolsExt.h>
+struct PyciRange {
+    explicit PyciRange(const char *name) { nvtxRangePushA(name); }
+    ~PyciRange() { nvtxRangePop(); }
+    PyciRange(const PyciRange &) = delete;
+    PyciRange &operator=(const PyciRange &) = delete;
+};
+#define PYCI_CAT2(a, b) a##b
+#define PYCI_CAT(a, b) PYCI_CAT2(a, b)
+#define PYCI_NVTX(name) PyciRange PYCI_CAT(pyci_range_, __LINE__)(name)
+
 typedef unsigned long long u64;
 typedef unsigned int u32;
 

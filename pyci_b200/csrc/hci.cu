@@ -616,6 +616,7 @@ int upload_coeffs(pyci_ctx *ctx, const double *coeffs, long ndet, double **dc) {
 // order), rebuilds its index, and reports how many were added.
 int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double *coeffs, double eps, long *n_new,
                  double *seconds) {
+    PYCI_NVTX("pyci:add_hci");
     double *dc = nullptr;
     ExtList L;
     u32 *order_in = nullptr, *order_out = nullptr;
@@ -676,6 +677,7 @@ int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double
 // compute_enpt2 (enpt2.cpp:344-374) for FullCI / GenCI wave functions
 int enpt2_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const double *coeffs, double energy, double eps,
                double *out, long *nterms, double *seconds) {
+    PYCI_NVTX("pyci:compute_enpt2");
     double *dc = nullptr, *acc = nullptr;
     ExtList L;
     auto body = [&]() -> int {

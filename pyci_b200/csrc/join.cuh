@@ -389,6 +389,7 @@ int join_run(pyci_ctx *ctx, const pyci_wfn *wfn, const BuildParams &P, uint2 *hi
     constexpr int NW = (KIND == PYCI_FULLCI) ? 2 : 1;
     cudaStream_t st = ctx->stream;
     *used = 0;
+    PYCI_NVTX("pyci:join(segment pairs)");
     const long ndet = wfn->ndet;
     if (ndet <= 0 || P.nloc <= 0)
         return PYCI_OK;

@@ -460,6 +460,7 @@ int trdm_dispatch(pyci_ctx *ctx, const pyci_wfn *wfn2, BuildParams &P, const dou
 } // namespace
 
 int rdms_impl(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2) {
+    PYCI_NVTX("pyci:compute_rdms");
     BuildParams P;
     PYCI_TRY(enum_params_init(P, wfn));
     const long n = wfn->nbasis, n2 = n * n, n4 = n2 * n2;

@@ -109,6 +109,28 @@ __global__ void __launch_bounds__(RB) ritz_residual_kernel(const double *__restr
     }
 }
 
+// Thick restart, in place: V_r <- sum_j Z[j][r] V_j for r < kk, vectors V_j = V + j * ld, j < m <= ROT_MAXM.  Every
+// thread reads the m values of its element before it writes the kk <= m new ones.
+constexpr int ROT_MAXM = 64;
+__global__ void __launch_bounds__(RB) rotate_kernel(double *__restrict__ V, long ld, int m, int kk,
+                                                    const double *__restrict__ Z, long n) {
+    extern __shared__ double sh[]; // Z[m][m], row j = coefficients of V_j
+    for (int t = threadIdx.x; t < m * m; t += RB)
+        sh[t] = Z[t];
+    __syncthreads();
+    double v[ROT_MAXM];
+    for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB) {
+        for (int j = 0; j < m; ++j)
+            v[j] = V[j * ld + i];
+        for (int r = 0; r < kk; ++r) {
+            double a = 0.0;
+            for (int j = 0; j < m; ++j)
+                a = fma(sh[j * m + r], v[j], a);
+            V[r * ld + i] = a;
+        }
+    }
+}
+
 __global__ void scale_kernel(double *x, double alpha, long n) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         x[i] *= alpha;
@@ -194,6 +216,7 @@ struct Solver {
     double *V = nullptr, *W = nullptr, *X = nullptr, *AX = nullptr, *T = nullptr;
     double *xfull = nullptr; // all-gather target (R > 1)
     double *dsmall = nullptr; // device scratch for dots / coefficients
+    double *dZ = nullptr, *hZ = nullptr; // projected eigenvectors of a thick restart
     double *hsmall = nullptr; // pinned host mirror (results of dots)
     double *hring = nullptr, *dring = nullptr; // coefficient staging ring: RING slots of small_cap doubles, host pinned
                                                // + device, so that uploads need no synchronisation before reuse
@@ -211,6 +234,9 @@ struct Solver {
         dev_free(T);
         dev_free(xfull);
         dev_free(dsmall);
+        dev_free(dZ);
+        if (hZ)
+            cudaFreeHost(hZ);
         if (hsmall)
             cudaFreeHost(hsmall);
         if (hring)
@@ -227,6 +253,7 @@ struct Solver {
         PYCI_CUDA(cudaEventRecord(e0, st));
         const double *xin = v;
         if (R > 1) {
+            PYCI_NVTX("pyci:allgather(trial vector)");
             PYCI_TRY(comm_allgather_f64(ctx, v, xfull, ld));
             xin = xfull;
         }
@@ -356,6 +383,7 @@ struct Solver {
 
 int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, double tol, double *evals,
                double *evecs, pyci_solve_stats *stats_out) {
+    PYCI_NVTX("pyci:solve(davidson)");
     pyci_ctx *ctx = op->ctx;
     const long nrow = op->nrow;
     const int R = ctx->nranks;
@@ -394,6 +422,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     PYCI_CUDA(dev_malloc(&S.xfull, vec * R));
     PYCI_CUDA(dev_malloc(&S.dsmall, sizeof(double) * S.small_cap));
     PYCI_CUDA(cudaMallocHost(&S.hsmall, sizeof(double) * S.small_cap));
+    PYCI_CUDA(dev_malloc(&S.dZ, sizeof(double) * (size_t)mmax * mmax));
+    PYCI_CUDA(cudaMallocHost(&S.hZ, sizeof(double) * (size_t)mmax * mmax));
     PYCI_CUDA(cudaMallocHost(&S.hring, sizeof(double) * S.small_cap * Solver::RING));
     PYCI_CUDA(dev_malloc(&S.dring, sizeof(double) * S.small_cap * Solver::RING));
     PYCI_CUDA(cudaEventCreate(&S.e0));
@@ -449,6 +479,11 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     std::vector<double> rn(nroot, 0.0);
     std::vector<char> conv(nroot, 0);
     const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+    // Ritz vectors kept by a restart: half the subspace (PYCI_B200_SOLVER_KEEP overrides; 0 = the wanted ones only)
+    int keep_target = std::max(nroot, mmax / 2);
+    if (const char *e = getenv("PYCI_B200_SOLVER_KEEP"))
+        keep_target = std::max(nroot, std::min(mmax - nroot, atoi(e)));
+    keep_target = std::min(keep_target, mmax - nroot);
     bool done = false;
     double spmv_ms = 0.0;
     long iter = 0;
@@ -520,12 +555,27 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
         for (int r = 0; r < nr; ++r)
             nunconv += !conv[r];
         if (m + nunconv > mmax) {
-            PYCI_CUDA(cudaMemcpyAsync(S.V, S.X, vec * nr, cudaMemcpyDeviceToDevice, S.st));
-            PYCI_CUDA(cudaMemcpyAsync(S.W, S.AX, vec * nr, cudaMemcpyDeviceToDevice, S.st));
+            // Thick restart: keep the lowest `keep` Ritz vectors (the wanted ones first), not only the wanted ones --
+            // collapsing to the current approximation throws the Krylov information of the subspace away and costs
+            // two to three times the matvecs on dense spectra (config 5).  V <- V Z, W <- W Z in place, G = diag(theta).
+            int keep = std::max(nr, std::min(m - 1, keep_target));
+            if (m > ROT_MAXM)
+                keep = nr;
+            if (keep > nr) {
+                std::memcpy(S.hZ, Z.data(), sizeof(double) * (size_t)m * m);
+                PYCI_CUDA(cudaMemcpyAsync(S.dZ, S.hZ, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, S.st));
+                rotate_kernel<<<S.grid, RB, sizeof(double) * (size_t)m * m, S.st>>>(S.V, S.ld, m, keep, S.dZ, S.nloc);
+                rotate_kernel<<<S.grid, RB, sizeof(double) * (size_t)m * m, S.st>>>(S.W, S.ld, m, keep, S.dZ, S.nloc);
+                ctx->launches += 2;
+                PYCI_CUDA(cudaStreamSynchronize(S.st)); // hZ is reused by the next restart
+            } else {
+                PYCI_CUDA(cudaMemcpyAsync(S.V, S.X, vec * nr, cudaMemcpyDeviceToDevice, S.st));
+                PYCI_CUDA(cudaMemcpyAsync(S.W, S.AX, vec * nr, cudaMemcpyDeviceToDevice, S.st));
+            }
             std::fill(G.begin(), G.end(), 0.0);
-            for (int r = 0; r < nr; ++r)
+            for (int r = 0; r < keep; ++r)
                 G[(size_t)r * mmax + r] = theta[r];
-            m = nr;
+            m = keep;
             S.stats.restarts++;
         }
         // expand

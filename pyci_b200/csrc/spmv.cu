@@ -405,6 +405,7 @@ int stream_launch(pyci_op *op, const double *x_dev, double *y_dev) {
 } // namespace
 
 int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
+    PYCI_NVTX("pyci:spmv");
     pyci_ctx *ctx = op->ctx;
     if (op->nloc <= 0)
         return PYCI_OK;
