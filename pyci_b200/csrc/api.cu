@@ -341,14 +341,8 @@ int pyci_wfn_create_all_dets(pyci_ctx *ctx, int kind, long nbasis, long nocc_up,
     pyci_wfn *wfn = wfn_new(ctx, kind, nbasis, nocc_up, nocc_dn, ndet);
     int rc = wfn_generate_all_dets(wfn, binom_l(nbasis, nocc_up), kind == PYCI_FULLCI ? binom_l(nbasis, nocc_dn) : 1);
     if (rc == PYCI_OK) {
-        if (kind == PYCI_FULLCI && !getenv("PYCI_B200_EAGER_INDEX")) {
-            // add_all_dets order and valid occupations by construction: nothing to check, the hash index is deferred
-            wfn->sorted2 = true;
-            wfn->index_valid = false;
-            wfn->hash_seconds = 0.0;
-        } else {
-            rc = wfn_build_index(wfn);
-        }
+        wfn->generated = true; // add_all_dets order and valid occupations by construction (wfn_build_index)
+        rc = wfn_build_index(wfn);
     }
     if (rc != PYCI_OK) {
         pyci_wfn_destroy(wfn);

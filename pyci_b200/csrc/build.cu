@@ -264,7 +264,10 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         if (threadIdx.x == 0)
             low_count = 0;
         __syncthreads();
-        if (KIND != PYCI_DOCI)
+        const int ndiag = (row < P.ncol) ? 1 : 0; // the diagonal takes slot 0 below
+        const int nh = (int)(P.indptr[r + 1] - P.indptr[r]) - ndiag;
+        const bool recorded = hitlist != nullptr && nh <= cap; // hits of this row were recorded by the count pass
+        if (KIND != PYCI_DOCI && !recorded)
             build_tables<KIND, true>(P, rs, T, nSa, nSb);
         if (threadIdx.x == 0 && row < P.ncol) { // diagonal, sparseop.cpp:252-255 / :421-424 / :496-499
             const int slot = atomicAdd(&rs.count, 1);
@@ -274,16 +277,12 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         }
         __syncthreads();
         int nlow = 0;
-        const int ndiag = (row < P.ncol) ? 1 : 0; // the diagonal took slot 0 above
-        const int nh = (int)(P.indptr[r + 1] - P.indptr[r]) - ndiag;
-        if (hitlist != nullptr && nh <= cap) {
-            // sparse row recorded by the count pass: evaluate the hits only (no enumeration, no probes)
+        if (recorded) {
+            // sparse row recorded by the count pass: evaluate the hits only (no enumeration, no probes, no tables)
             const uint2 *hrow = hitlist + (size_t)r * cap;
             for (int k = threadIdx.x; k < nh; k += blockDim.x) {
                 const uint2 h = hrow[k];
-                u64 A, B;
-                double v;
-                candidate<KIND, true>(P, rs, T, pairs, h.x, A, B, v);
+                const double v = hit_element<KIND>(P, rs, pairs, h.x);
                 const int slot = ndiag + k;
                 keyA[slot] = ((u64)h.y << 32) | (u32)slot;
                 valbuf[slot] = v;
@@ -594,6 +593,8 @@ double binom_d(long n, long k) {
 }
 
 // complete sorted two-spin space: string tables for both spins, then the segment-ordered fill (build_complete.cuh)
+// one allocation per spin (T.cr heads it): fifteen stream-ordered allocations per spin cost more host time than the
+// string-table kernels take on the device
 int alloc_string_tables(StringTables &T, u32 N, u32 L, u32 L1, u32 nocc, u32 nS, u32 nD) {
     T.N = N;
     T.L = L;
@@ -603,29 +604,34 @@ int alloc_string_tables(StringTables &T, u32 N, u32 L, u32 L1, u32 nocc, u32 nS,
     T.nD = nD;
     const size_t e = (size_t)N * L, e1 = (size_t)N * L1, eS = std::max<size_t>((size_t)N * nS, 1),
                  eD = std::max<size_t>((size_t)N * nD, 1);
-    PYCI_CUDA(dev_malloc(&T.cr, 4 * e));
-    PYCI_CUDA(dev_malloc(&T.dval, 8 * e));
-    PYCI_CUDA(dev_malloc(&T.sub, 8 * e1));
-    PYCI_CUDA(dev_malloc(&T.pos1, 4 * e1));
-    PYCI_CUDA(dev_malloc(&T.terms, 8 * e1 * std::max<u32>(nocc, 1)));
-    PYCI_CUDA(dev_malloc(&T.j1self, 4 * (size_t)N));
-    PYCI_CUDA(dev_malloc(&T.selfj, 4 * (size_t)N));
-    PYCI_CUDA(dev_malloc(&T.s_off, 4 * eS));
-    PYCI_CUDA(dev_malloc(&T.s_aux, 4 * eS));
-    PYCI_CUDA(dev_malloc(&T.s_cr, 4 * eS));
-    PYCI_CUDA(dev_malloc(&T.s_pre, 8 * eS));
-    PYCI_CUDA(dev_malloc(&T.d_off, 4 * eD));
-    PYCI_CUDA(dev_malloc(&T.d_cr, 4 * eD));
-    PYCI_CUDA(dev_malloc(&T.d_val, 8 * eD));
-    PYCI_CUDA(dev_malloc(&T.self_off, 4 * (size_t)N));
+    const size_t sizes[15] = {4 * e, 8 * e, 8 * e1, 4 * e1, 8 * e1 * std::max<u32>(nocc, 1), 4 * (size_t)N, 4 * (size_t)N,
+                              4 * eS, 4 * eS, 4 * eS, 8 * eS, 4 * eD, 4 * eD, 8 * eD, 4 * (size_t)N};
+    size_t off[16];
+    off[0] = 0;
+    for (int q = 0; q < 15; ++q)
+        off[q + 1] = off[q] + ((sizes[q] + 255) & ~(size_t)255);
+    unsigned char *base = nullptr;
+    PYCI_CUDA(dev_malloc(&base, off[15]));
+    T.cr = reinterpret_cast<u32 *>(base + off[0]);
+    T.dval = reinterpret_cast<double *>(base + off[1]);
+    T.sub = reinterpret_cast<uint2 *>(base + off[2]);
+    T.pos1 = reinterpret_cast<u32 *>(base + off[3]);
+    T.terms = reinterpret_cast<double *>(base + off[4]);
+    T.j1self = reinterpret_cast<u32 *>(base + off[5]);
+    T.selfj = reinterpret_cast<u32 *>(base + off[6]);
+    T.s_off = reinterpret_cast<u32 *>(base + off[7]);
+    T.s_aux = reinterpret_cast<u32 *>(base + off[8]);
+    T.s_cr = reinterpret_cast<u32 *>(base + off[9]);
+    T.s_pre = reinterpret_cast<double *>(base + off[10]);
+    T.d_off = reinterpret_cast<u32 *>(base + off[11]);
+    T.d_cr = reinterpret_cast<u32 *>(base + off[12]);
+    T.d_val = reinterpret_cast<double *>(base + off[13]);
+    T.self_off = reinterpret_cast<u32 *>(base + off[14]);
     return PYCI_OK;
 }
 
 void free_string_tables(StringTables &T) {
-    void *ptrs[] = {T.cr, T.dval, T.sub, T.pos1, T.terms, T.j1self, T.selfj, T.s_off, T.s_aux, T.s_cr, T.s_pre,
-                    T.d_off, T.d_cr, T.d_val, T.self_off};
-    for (void *q : ptrs)
-        dev_free(q);
+    dev_free(T.cr); // heads the single allocation
     memset(&T, 0, sizeof(T));
 }
 
@@ -816,8 +822,9 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     PYCI_NVTX("pyci:fill");
 
     op->nnz = nnz;
-    PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)(nnz + 4))); // +4: 16-byte bulk reads may overrun the end
-    PYCI_CUDA(dev_malloc(&op->vals, sizeof(double) * (size_t)(nnz + 4)));
+    // the larger array first: a pool that holds the blocks of a destroyed operator hands them back in matching sizes
+    PYCI_CUDA(dev_malloc(&op->vals, sizeof(double) * (size_t)(nnz + 4))); // +4: 16-byte bulk reads may overrun the end
+    PYCI_CUDA(dev_malloc(&op->cols, sizeof(int) * (size_t)(nnz + 4)));
     P.cols = op->cols;
     P.vals = op->vals;
     P.maxrow = (maxrow + 1) & ~1;
@@ -1104,6 +1111,13 @@ int wfn_ensure_index(const pyci_wfn *wfn) {
 int wfn_build_index(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
     PYCI_NVTX("pyci:index(check)");
+    if (wfn->generated && wfn->kind == PYCI_FULLCI && wfn->complete && !getenv("PYCI_B200_EAGER_INDEX")) {
+        // unranked on the device in add_all_dets order (pyci_wfn_create_all_dets): sorted, valid and complete by
+        // construction -- nothing to check, and the hash index stays deferred (or valid, if something built it)
+        wfn->sorted2 = true;
+        wfn->hash_seconds = 0.0;
+        return PYCI_OK;
+    }
     dev_free(wfn->slots);
     wfn->slots = nullptr;
     wfn->index_valid = false;

@@ -92,6 +92,7 @@ struct pyci_wfn {
     int nwords = 1;       // u64 words per determinant in `dets` (1 one-spin, 2 two-spin)
     int keymode = KEY64;
     bool complete = false; // ndet equals the size of the full space => every excitation is present
+    bool generated = false; // determinants unranked on the device (pyci_wfn_create_all_dets), never appended to
     bool sorted2 = false;  // two-spin determinants ascend in (alpha, beta) as integers (add_all_dets order)
     u64 *dets = nullptr;   // [ndet][nwords]
     void *slots = nullptr; // hash slots (layout by keymode)

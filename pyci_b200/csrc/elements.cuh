@@ -213,4 +213,60 @@ __device__ __forceinline__ void candidate(const BuildParams &P, const RowShared 
         val = T.sb_val[c];
 }
 
+// Signed matrix element of candidate c of the row WITHOUT the per-row single-excitation tables: for rows whose few
+// stored entries are already known (recorded hits of a selected space), where building the tables -- every single
+// excitation of the row, nocc two-electron terms each -- would cost far more than the entries themselves.  Same
+// operations in the same order as build_tables / candidate (sparseop.cpp:303-315,318-337,339-358,382-416,459-490).
+template<int KIND>
+__device__ __forceinline__ double hit_element(const BuildParams &P, const RowShared &rs, const uchar2 *__restrict__ pairs,
+                                              u32 c) {
+    const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
+    u64 A, B;
+    u32 code;
+    decode<KIND>(P, rs, pairs, c, A, B, code);
+    const int type = code >> 24;
+    const long i = (code >> 18) & 63, a = (code >> 12) & 63, k = (code >> 6) & 63, l = code & 63;
+    const int na = rs.nocc[0], nb = (KIND == PYCI_FULLCI) ? rs.nocc[1] : 0;
+    switch (type) {
+    case T_PAIR:
+        return __ldg(P.v + i * n1 + a);
+    case T_AB: {
+        const int par = parity_single(rs.det[0], (int)i, (int)a) ^ parity_single(rs.det[1], (int)k, (int)l);
+        return apply_sign(__ldg(P.two_mo + ((u32)(n3 * i + n1 * a) + (u32)(n2 * k + l))), par);
+    }
+    case T_AA:
+    case T_BB: {
+        const long koff = n3 * i + n2 * k;
+        const double x = __ldg(P.two_mo + koff + n1 * a + l) - __ldg(P.two_mo + koff + n1 * l + a);
+        return apply_sign(x, parity_double(rs.det[type == T_AA ? 0 : 1], (int)i, (int)k, (int)a, (int)l));
+    }
+    case T_SA: {
+        const long ioff = n3 * i;
+        double val1 = __ldg(P.one_mo + n1 * i + a);
+        for (int q = 0; q < na; ++q) {
+            const long kk = rs.occ[0][q], koff = ioff + n2 * kk;
+            val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
+        }
+        for (int q = 0; q < nb; ++q) {
+            const long kk = rs.occ[1][q];
+            val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
+        }
+        return apply_sign(val1, parity_single(rs.det[0], (int)i, (int)a));
+    }
+    default: { // T_SB
+        const long ioff = n3 * i;
+        double val1 = __ldg(P.one_mo + n1 * i + a);
+        for (int q = 0; q < na; ++q) {
+            const long kk = rs.occ[0][q];
+            val1 += __ldg(P.two_mo + ioff + n2 * kk + n1 * a + kk);
+        }
+        for (int q = 0; q < nb; ++q) {
+            const long kk = rs.occ[1][q], koff = ioff + n2 * kk;
+            val1 += __ldg(P.two_mo + koff + n1 * a + kk) - __ldg(P.two_mo + koff + n1 * kk + a);
+        }
+        return apply_sign(val1, parity_single(rs.det[1], (int)i, (int)a));
+    }
+    }
+}
+
 } // namespace

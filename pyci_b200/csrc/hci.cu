@@ -19,9 +19,8 @@
 #include <cstring>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include "elements.cuh"
+#include "radix.cuh"
 
 namespace {
 
@@ -637,13 +636,13 @@ int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double
         PYCI_CUDA(dev_malloc(&keys_out, sizeof(u64) * (size_t)n));
         iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(order_in, n);
         ctx->launches++;
-        size_t tmp_bytes = 0;
-        PYCI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, L.pay, keys_out, order_in, order_out, (int)n, 0, 64,
-                                                  ctx->stream));
-        PYCI_CUDA(dev_malloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
-        PYCI_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, L.pay, keys_out, order_in, order_out, (int)n, 0, 64,
-                                                  ctx->stream));
-        ctx->launches += 4;
+        bool in_alt = false;
+        int pbits = 25; // payload = row << 24 | position in the row's loop nest
+        while ((1L << (pbits - 24)) < wfn->ndet)
+            ++pbits;
+        PYCI_TRY(radix_sort_pairs<u32>(ctx, L.pay, keys_out, order_in, order_out, n, pbits, &in_alt));
+        if (!in_alt)
+            std::swap(order_in, order_out); // ext_gather_dets_kernel reads order_out
         // grow the determinant array and append
         const int nw = wfn->nwords;
         PYCI_CUDA(dev_malloc(&newdets, sizeof(u64) * (size_t)((wfn->ndet + n) * nw)));
@@ -661,6 +660,7 @@ int add_hci_impl(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const double
         dev_free(wfn->slots);
         wfn->slots = nullptr;
         wfn->index_valid = false;
+        wfn->generated = false;
         return PYCI_OK;
     };
     int rc = body();

@@ -18,9 +18,7 @@
 // triangle) is bit-identical to a fresh build: rows < n0 export only columns <= row, which are untouched.
 #include <algorithm>
 
-#include <cub/device/device_radix_sort.cuh>
-
-#include "common.cuh"
+#include "radix.cuh"
 
 namespace {
 
@@ -199,11 +197,12 @@ int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci
             int bits = 1;
             while ((1L << bits) < n1)
                 ++bits;
-            size_t tmp_bytes = 0;
-            PYCI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, tkeys, tkeys2, tvals, tvals2, (int)nt, 0, 32 + bits, st));
-            PYCI_CUDA(dev_malloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
-            PYCI_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, tkeys, tkeys2, tvals, tvals2, (int)nt, 0, 32 + bits, st));
-            ctx->launches += 4;
+            bool in_alt = false;
+            PYCI_TRY(radix_sort_pairs<double>(ctx, tkeys, tkeys2, tvals, tvals2, nt, 32 + bits, &in_alt));
+            if (!in_alt) { // place_transposed_kernel reads the *2 buffers
+                std::swap(tkeys, tkeys2);
+                std::swap(tvals, tvals2);
+            }
             place_transposed_kernel<<<gsz, 256, 0, st>>>(tkeys2, tvals2, nt, addptr, nip, op->indptr, ncols, nvals);
             ctx->launches++;
         }

@@ -223,9 +223,9 @@ def test_config4_one_gpu_and_its_shards(cabi, ctx):
     bench builds) bit-exact against the oracle; the SpMV of a shard equals the same rows of the whole product."""
     import torch
     n, occ = 16, (4, 4)
-    free, _ = torch.cuda.mem_get_info(0)
-    if free < 150e9:
-        pytest.skip("needs ~150 GB of free HBM")
+    _, total = torch.cuda.mem_get_info(0)
+    if total < 170e9:
+        pytest.skip("needs a 180 GB device")
     ecore, one, two = O.synthetic_integrals(n, 1234)
     dets = O.all_dets(O.FULLCI, n, *occ)
     ndet, nb = len(dets), 1820
@@ -236,7 +236,7 @@ def test_config4_one_gpu_and_its_shards(cabi, ctx):
     x = torch.from_numpy(seeded_vec(ndet, 8)).cuda()
     op = cabi.Op(ctx, ham, w)
     assert op.fill_kernel() == "fill_complete_kernel" and op.stored_nnz == ndet * 3193
-    rows = sample_rows(0, ndet, nb, rng, 700)
+    rows = sample_rows(0, ndet, nb, rng, 900)
     assert len(rows) >= 1000
     assert_rows_equal(op, rows, O.FULLCI, n, occ, dets, (one, two))
     y = torch.empty(ndet, dtype=torch.float64, device="cuda")
