@@ -238,13 +238,16 @@ __device__ u64 *block_radix_sort(u64 *a, u64 *b, int m, int passes, int dbits, u
 // hitlist != nullptr: rows whose hits were recorded by the count pass (at most `cap`) are assembled from the record.
 template<int KIND, int KM, bool LAZY>
 __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb,
-                                                   const uint2 *__restrict__ hitlist, int cap) {
+                                                   const uint2 *__restrict__ hitlist, int cap, u64 *gscratch,
+                                                   int short_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: keys A | keys B | values | radix counters | excitation tables | pair table
-    u64 *keyA = reinterpret_cast<u64 *>(smem_raw);
+    // layout: keys A | keys B | values | radix counters | excitation tables | pair table.  Rows of more than
+    // `short_cap` entries (a few dominant determinants of a heat-bath space reach 10^4) do not fit shared memory:
+    // a second launch (gscratch != nullptr) builds exactly those, with the three row buffers in a per-CTA slab of HBM.
+    u64 *keyA = gscratch ? gscratch + (size_t)blockIdx.x * 3 * (size_t)P.maxrow : reinterpret_cast<u64 *>(smem_raw);
     u64 *keyB = keyA + P.maxrow;
     double *valbuf = reinterpret_cast<double *>(keyB + P.maxrow);
-    u32 *hist = reinterpret_cast<u32 *>(valbuf + P.maxrow);
+    u32 *hist = gscratch ? reinterpret_cast<u32 *>(smem_raw) : reinterpret_cast<u32 *>(valbuf + P.maxrow);
     const int nbins = 1 << P.sort_dbits, nw = blockDim.x >> 5;
     u32 *tot = hist + nw * nbins;
     unsigned char *tbase = reinterpret_cast<unsigned char *>(tot + nbins);
@@ -259,6 +262,11 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
     const u32 lt = (1u << lane) - 1u;
     for (long r = blockIdx.x; r < P.nloc; r += gridDim.x) {
         const long row = P.row0 + r;
+        {
+            const long len = P.indptr[r + 1] - P.indptr[r];
+            if (gscratch ? len <= (long)short_cap : len > (long)short_cap)
+                continue; // the other launch's row (uniform over the CTA)
+        }
         __syncthreads();
         row_setup(rs, P, row, nspin);
         if (threadIdx.x == 0)
@@ -678,6 +686,8 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.nn = (u32)(P.n * P.n);
     C.GP = std::max(1u, 256u / L1b);
     C.GPnn = C.GP * C.nn;
+    C.GPw = std::max(1u, 192u / L1b);
+    C.GPwnn = C.GPw * C.nn;
     C.dL1b = make_fastdiv(L1b);
     PYCI_CUDA(cudaFuncSetAttribute(string_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     string_table_kernel<<<std::min<u32>(Na, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.A, 0, (long)Nb, S.Wa, S.K1, S.binom,
@@ -687,12 +697,17 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     ctx->launches += 2;
     const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
     PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
+    // PYCI_B200_FILL_V1: the first form of the kernel (every warp passes through every segment) instead of the
+    // warp-specialised one; both write the same bytes
+    const bool v1 = getenv("PYCI_B200_FILL_V1") != nullptr;
     if (with_slice) {
-        PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        fill_complete_kernel<true><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
+        auto k = v1 ? fill_complete_kernel<true> : fill_complete_ws_kernel<true>;
+        PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     } else {
-        PYCI_CUDA(cudaFuncSetAttribute(fill_complete_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        fill_complete_kernel<false><<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
+        auto k = v1 ? fill_complete_kernel<false> : fill_complete_ws_kernel<false>;
+        PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
     ctx->launches++;
@@ -837,6 +852,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
         P.sort_dbits = std::max(5, (bits + P.sort_passes - 1) / P.sort_passes);
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[2], st)); // after the allocations: ev[2]..ev[3] brackets kernels only
+    u64 *long_scratch = nullptr; // row buffers in HBM for rows too long for shared memory (freed after the fill)
     std::vector<u32> hb; // binomial table staged for the string-table pre-pass (lives until the final synchronise)
     bool fill_timed = false;
     if (nloc > 0 && nnz > 0) {
@@ -910,40 +926,62 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             PYCI_TRY(wfn_ensure_index(wfn));
             ix = make_index<KM>(wfn);
             int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
-            size_t smem = 0;
-            for (;;) { // keys (ping-pong) + values + radix counters + tables + pair table
-                smem = (size_t)24 * P.maxrow + sizeof(u32) * ((size_t)(block / 32) + 1) * (1u << P.sort_dbits) +
-                       tab_bytes + pair_bytes;
-                if ((long)smem <= (long)ctx->smem_optin || block == 32)
-                    break;
+            // keys (ping-pong) + values + radix counters + tables + pair table
+            auto smem_for = [&](int blk, long rows) {
+                return (size_t)24 * (size_t)rows + sizeof(u32) * ((size_t)(blk / 32) + 1) * (1u << P.sort_dbits) + tab_bytes +
+                       pair_bytes;
+            };
+            const int full_rows = P.maxrow;
+            while (block > 32 && (long)smem_for(block, full_rows) > (long)ctx->smem_optin)
                 block >>= 1;
+            int short_cap = full_rows; // longest row built in shared memory
+            // PYCI_B200_SHORT_CAP=k: send rows of more than k entries through the HBM launch regardless (tests)
+            const long forced_cap = getenv("PYCI_B200_SHORT_CAP") ? std::max(2L, atol(getenv("PYCI_B200_SHORT_CAP"))) : 0;
+            const bool long_rows = (long)smem_for(block, full_rows) > (long)ctx->smem_optin ||
+                                   (forced_cap > 0 && forced_cap < full_rows);
+            if (long_rows) {
+                // a few rows are too long for shared memory: those go through HBM in a second launch
+                block = pick_block((long)P.ncand / 4);
+                const long fit = ((long)ctx->smem_optin - (long)smem_for(block, 0) - 1024) / 24;
+                if (fit < 64)
+                    PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "excitation tables (%zu bytes) leave no room for a row buffer",
+                              smem_for(block, 0));
+                short_cap = (int)(std::min<long>(fit, forced_cap > 0 ? forced_cap : 4096) & ~1L);
             }
-            if ((long)smem > (long)ctx->smem_optin)
-                PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
-                          "a matrix row holds %d entries; rows above %ld entries do not fit the shared-memory row buffer",
-                          maxrow, (long)((ctx->smem_optin - tab_bytes - pair_bytes - 2048) / 24));
+            const size_t smem = smem_for(block, short_cap);
             // most candidates miss (selected space): evaluate elements for hits only
             const bool lazy = !analytic && (double)nnz < 0.25 * (double)nloc * ((double)P.ncand + 1.0);
-            int per_sm = 1;
             PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
             fill_timed = true;
-            if (lazy) {
-                PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, true>, block, smem));
+            auto launch = [&](auto kern) -> int {
+                int per_sm = 1;
+                BuildParams Ps = P;
+                Ps.maxrow = short_cap;
+                PYCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                fill_kernel<KIND, KM, true><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
-            } else {
-                PYCI_CUDA(cudaFuncSetAttribute(fill_kernel<KIND, KM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_kernel<KIND, KM, false>, block, smem));
-                const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                fill_kernel<KIND, KM, false><<<(unsigned)grid, block, smem, st>>>(P, ix, nSa, nSb, hitlist, hitcap);
-            }
+                kern<<<(unsigned)grid, block, smem, st>>>(Ps, ix, nSa, nSb, hitlist, hitcap, nullptr, short_cap);
+                ctx->launches++;
+                if (long_rows) {
+                    const size_t smem2 = smem_for(block, 0);
+                    PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem2));
+                    const long grid2 = std::min<long>(nloc, (long)ctx->sm_count * std::min(std::max(per_sm, 1), 2));
+                    PYCI_CUDA(dev_malloc(&long_scratch, sizeof(u64) * 3 * (size_t)full_rows * (size_t)grid2));
+                    kern<<<(unsigned)grid2, block, smem2, st>>>(P, ix, nSa, nSb, hitlist, hitcap, long_scratch, short_cap);
+                    ctx->launches++;
+                }
+                return PYCI_OK;
+            };
+            if (lazy)
+                PYCI_TRY(launch(fill_kernel<KIND, KM, true>));
+            else
+                PYCI_TRY(launch(fill_kernel<KIND, KM, false>));
             PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
-            ctx->launches++;
             op->fill_kernel = "fill_kernel";
         }
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[3], st));
+    dev_free(long_scratch);
     dev_free(hitlist);
     PYCI_CUDA(cudaStreamSynchronize(st));
     PYCI_CUDA(cudaGetLastError());

@@ -50,6 +50,7 @@ struct CompleteParams {
     FastDiv dSb;
     // launch-time constants of the fill kernel (kept out of registers: the compiler re-derives them per use)
     u32 nn, GP, GPnn; // n^2; walkers side by side in the alpha-beta segment = max(1, 256 / L1b); GP * n^2
+    u32 GPw, GPwnn;   // the same for the warp-specialised kernel (192 alpha-beta threads per group)
     FastDiv dL1b;     // division of the thread index by L1b
 };
 
@@ -479,6 +480,264 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
         }
     }
     if ((threadIdx.x & 255u) == 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all rows written before the CTA retires
+}
+
+
+// ---- warp-specialised form ------------------------------------------------------------------------------------------
+// Same row layout, tables and shared-memory staging as fill_complete_kernel, but the eight warps of a group keep
+// FIXED ROLES for every row instead of all passing through every segment's code with most lanes idle:
+//   warps 0-5  the A' = A group (columns of the whole beta list, values of its doubles; its global loads are issued
+//              before the row barrier, two entries per thread) and the alpha-beta doubles (72-76 % of a row):
+//              192 / L1b walkers side by side
+//   warp  6    the beta singles and the diagonal
+//   warp  7    alpha-alpha doubles, alpha singles, then -- after the FULL barrier -- the two bulk stores of the row
+// A role's per-row set-up is only what that role needs, so the straight-line overhead that every warp used to pay
+// for every segment (three quarters of the instructions of fill_complete_kernel, ncu r1u) is paid once per row.
+template<bool SLICE>
+__global__ void __launch_bounds__(1024, 1) fill_complete_ws_kernel(BuildParams P, CompleteParams C, int G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
+    const u32 nn = C.nn;
+    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
+    uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
+    uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
+    double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
+    double *d_val = s_pre + nSa;
+    double *JA = d_val + nDa; // [n][n] one_mo[i,a] + sum_{k in A} <ik|ak>
+    const double *slice = reinterpret_cast<const double *>(smem_raw + SL.tables); // [nSa][n][n]
+    const int group = threadIdx.x >> 8;
+    const u32 t = threadIdx.x & 255u, warp = t >> 5, lane = t & 31u;
+    double *sval = reinterpret_cast<double *>(smem_raw + SL.tables + SL.slice + (size_t)group * SL.rowbuf);
+    int *scol = reinterpret_cast<int *>(sval + SL.MP);
+
+    const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
+    const double *__restrict__ two_mo = P.two_mo;
+    const long per = (P.nloc + gridDim.x - 1) / gridDim.x;
+    const long rbeg = (long)blockIdx.x * per, rend = min(P.nloc, rbeg + per);
+    if (rbeg >= rend)
+        return;
+    // alpha-beta role: a thread keeps ONE entry of the beta sub-list and walks the alpha singles g = gq, gq + GP, ...
+    const u32 GP = C.GPw;
+    const u32 gq = (L1b <= 192u) ? fdiv(t, C.dL1b) : 0u;
+    const u32 w0 = (L1b <= 192u) ? t - gq * L1b : t;
+    const bool ab_active = (L1b > 192u) || gq < GP;
+    const u32 ra_first = (u32)((P.row0 + rbeg) / Nb), ra_last = (u32)((P.row0 + rend - 1) / Nb);
+    for (u32 ra = ra_first; ra <= ra_last; ++ra) {
+        // ---- stage the alpha string's tables (all threads of the CTA)
+        __syncthreads();
+        {
+            const u64 Adet = P.dets[2 * ((long)ra * Nb)];
+            const size_t bS = (size_t)ra * nSa, bD = (size_t)ra * nDa;
+            for (u32 g = threadIdx.x; g < nSa; g += blockDim.x) {
+                const u32 aux = C.A.s_aux[bS + g];
+                s_pack[g] = make_uint4(C.A.s_off[bS + g], C.A.s_cr[bS + g] * Nb, aux & 0x7fffffffu, aux & 0x80000000u);
+                s_pre[g] = C.A.s_pre[bS + g];
+            }
+            for (u32 d = threadIdx.x; d < nDa; d += blockDim.x) {
+                d_pack[d] = make_uint2(C.A.d_off[bD + d], C.A.d_cr[bD + d] * Nb);
+                d_val[d] = C.A.d_val[bD + d];
+            }
+            for (u32 q = threadIdx.x; q < nn; q += blockDim.x) { // sparseop.cpp:382-388
+                const long i = q / (u32)n1, a = q - i * n1;
+                double v = P.one_mo[n1 * i + a];
+                for (u64 w = Adet; w; w &= w - 1) {
+                    const long kk = __ffsll((long long)w) - 1;
+                    v += two_mo[n3 * i + n2 * kk + n1 * a + kk];
+                }
+                JA[q] = v;
+            }
+            if (SLICE) {
+                double *wslice = const_cast<double *>(slice);
+                for (u32 q = threadIdx.x; q < nSa * nn; q += blockDim.x) {
+                    const u32 g = q / nn, kl = q - g * nn, k = kl / (u32)n1, l = kl - k * (u32)n1;
+                    wslice[q] = two_mo[(C.A.s_aux[bS + g] & 0x7fffffffu) + n2 * k + l];
+                }
+            }
+        }
+        const u32 self_off = C.A.self_off[ra], self_colbase = ra * Nb;
+        __syncthreads();
+        const long blo = max(rbeg, (long)ra * Nb - P.row0), bhi = min(rend, (long)(ra + 1) * Nb - P.row0);
+        u32 rb = (u32)(P.row0 + blo + group - (long)ra * Nb);
+        for (long r = blo + group; r < bhi; r += G, rb += (u32)G) {
+            const long out0 = r * (long)M; // complete space: every row holds M entries
+            const u32 ov = (u32)out0 & 1u, oc = (u32)out0 & 3u;
+            // row buffer shifted so that shared and global addresses share their 16-byte phase
+            double *bval = sval + ov;
+            int *bcol = scol + oc;
+            if (warp < 6u) {
+                // ================= warps 0-5: the A' = A group (columns of the whole beta list, values of its
+                // doubles, sparseop.cpp:397-416), then the alpha-beta doubles (:318-337).  Every global load of the
+                // row is issued before the barrier.
+                const u32 *__restrict__ crB = C.B.cr + rb * Lb;
+                const double *__restrict__ dvalB = C.B.dval + rb * Lb;
+                const uint2 *__restrict__ subB = C.B.sub + rb * L1b;
+                const u32 j1s = __ldg(C.B.j1self + rb);
+                uint2 eb = make_uint2(0u, 0u);
+                if (ab_active && w0 < L1b)
+                    eb = __ldg(subB + w0);
+                u32 cb[2] = {0u, 0u};
+                double dv[2] = {0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) // the first 384 entries of the beta list (the rest, if any, below)
+                    if (t + 192u * q < Lb) {
+                        cb[q] = __ldg(crB + t + 192u * q);
+                        dv[q] = __ldg(dvalB + t + 192u * q);
+                    }
+                bar_free_sync(group);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const u32 w = t + 192u * q;
+                    if (w < Lb) {
+                        bcol[self_off + w] = (int)(self_colbase + (cb[q] & 0x7fffffffu));
+                        if (cb[q] >> 31)
+                            bval[self_off + w] = dv[q];
+                    }
+                }
+                for (u32 w = t + 384u; w < Lb; w += 192u) {
+                    const u32 c2 = __ldg(crB + w);
+                    bcol[self_off + w] = (int)(self_colbase + (c2 & 0x7fffffffu));
+                    if (c2 >> 31)
+                        bval[self_off + w] = __ldg(dvalB + w);
+                }
+                if (ab_active) {
+                    for (u32 w = w0; w < L1b; w += 192) {
+                        if (w != w0)
+                            eb = __ldg(subB + w); // colex rank | parity << 31, n i + a << 18, n^2 i + a
+                        if (w == j1s)
+                            continue; // B' = B: the alpha single of warp 7
+                        const u32 kl = SLICE ? ((eb.y >> 18) & 0xfffu) : (eb.y & 0x3ffffu);
+                        const u32 sgn_b = eb.y & 0x80000000u, cr_b = eb.x;
+                        int *pc = bcol + w;
+                        double *pv = bval + w;
+                        const uint4 *pa = s_pack + gq;
+                        const double *psl = slice + gq * nn + kl;
+#pragma unroll 4
+                        for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += C.GPwnn) {
+                            const uint4 a = *pa;
+                            const double v = SLICE ? *psl : __ldg(two_mo + (a.z + kl));
+                            pc[a.x] = (int)(a.y + cr_b);
+                            pv[a.x] = flip_sign(v, a.w ^ sgn_b);
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_full_arrive(group);
+            } else if (warp == 6u) {
+                // ================= warp 6: values of the beta singles (:382-394) and of the diagonal (:421-424);
+                // two sub-list entries per lane are loaded before the barrier
+                const uint2 *__restrict__ subB = C.B.sub + rb * L1b;
+                const u32 j1s = __ldg(C.B.j1self + rb);
+                const double diag_r = __ldg(P.diag + r);
+                u32 ps[2] = {0u, 0u}, sg[2] = {0u, 0u};
+                double tq[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const u32 j1 = lane + 32u * z;
+                    if (j1 < L1b) {
+                        ps[z] = __ldg(C.B.pos1 + rb * L1b + j1);
+                        sg[z] = __ldg(subB + j1).y & 0x80000000u;
+                        const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
+#pragma unroll
+                        for (u32 q = 0; q < 4; ++q)
+                            if (q < nb)
+                                tq[z][q] = __ldg(tb + q);
+                    }
+                }
+                bar_free_sync(group);
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const u32 j1 = lane + 32u * z;
+                    if (j1 < L1b) {
+                        const u32 slot = self_off + (ps[z] & 0xffffu);
+                        if (j1 == j1s) {
+                            bval[slot] = diag_r;
+                        } else {
+                            const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
+                            double v = JA[ps[z] >> 16];
+#pragma unroll
+                            for (u32 q = 0; q < 4; ++q)
+                                if (q < nb)
+                                    v += tq[z][q];
+                            for (u32 q = 4; q < nb; ++q)
+                                v += __ldg(tb + q);
+                            bval[slot] = flip_sign(v, sg[z]);
+                        }
+                    }
+                }
+                for (u32 j1 = lane + 64u; j1 < L1b; j1 += 32) {
+                    const u32 p1 = __ldg(C.B.pos1 + rb * L1b + j1);
+                    const u32 slot = self_off + (p1 & 0xffffu);
+                    if (j1 == j1s) {
+                        bval[slot] = diag_r;
+                    } else {
+                        const u32 sgn1 = __ldg(subB + j1).y & 0x80000000u;
+                        const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
+                        double v = JA[p1 >> 16];
+                        for (u32 q = 0; q < nb; ++q)
+                            v += __ldg(tb + q);
+                        bval[slot] = flip_sign(v, sgn1);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_full_arrive(group);
+            } else {
+                // ================= warp 7: alpha-alpha doubles (:339-358), alpha singles (:303-315), bulk stores
+                const u64 Bdet = __ldg(P.dets + 2 * (P.row0 + r) + 1);
+                const u32 j1s = __ldg(C.B.j1self + rb);
+                // the bulk stores of the previous row must have read the buffer before it is overwritten
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                bar_free_sync(group);
+                for (u32 d = lane; d < nDa; d += 32) {
+                    const uint2 dp = d_pack[d];
+                    bcol[dp.x] = (int)(dp.y + rb);
+                    bval[dp.x] = d_val[d];
+                }
+                for (u32 g = lane; g < nSa; g += 32) {
+                    const uint4 a = s_pack[g];
+                    double v = s_pre[g];
+                    for (u64 q = Bdet; q; q &= q - 1) {
+                        const u32 kk = (u32)__ffsll((long long)q) - 1u;
+                        v += SLICE ? slice[g * nn + kk * (u32)n1 + kk] : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
+                    }
+                    const u32 slot = a.x + j1s;
+                    bcol[slot] = (int)(a.y + rb);
+                    bval[slot] = flip_sign(v, a.w);
+                }
+                // ---- the finished row goes out as two bulk copies (TMA): 16-byte aligned bodies of the value and
+                // column streams; the few entries before / after the aligned bodies by scalar stores
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_full_sync(group);
+                const u32 hv = ov, nv = (M - hv) >> 1;                    // values: pairs
+                const u32 hc = min(M, (4u - oc) & 3u), nc = (M - hc) >> 2; // columns: quads
+                if (lane == 0) {
+                    if (nv)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.vals + out0 + hv),
+                                     "r"((u32)__cvta_generic_to_shared(bval + hv)), "r"(nv * 16u)
+                                     : "memory");
+                    if (nc)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.cols + out0 + hc),
+                                     "r"((u32)__cvta_generic_to_shared(bcol + hc)), "r"(nc * 16u)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                // the few entries before / after the aligned bodies (read before this warp frees the buffer again)
+                if (lane >= 4 && lane < 4 + hv)
+                    P.vals[out0 + lane - 4] = bval[lane - 4];
+                if (lane >= 8 && lane - 8 + hv + 2 * nv < M)
+                    P.vals[out0 + hv + 2 * nv + lane - 8] = bval[hv + 2 * nv + lane - 8];
+                if (lane >= 12 && lane - 12 < hc)
+                    P.cols[out0 + lane - 12] = bcol[lane - 12];
+                if (lane >= 16 && lane < 20 && lane - 16 + hc + 4 * nc < M)
+                    P.cols[out0 + hc + 4 * nc + lane - 16] = bcol[hc + 4 * nc + lane - 16];
+                if (lane == 20)
+                    P.lowcnt[r] = (int)(self_off + __ldg(C.B.selfj + rb)) + 1; // slots up to and including the diagonal
+            }
+        }
+    }
+    if ((threadIdx.x & 255u) == 224u)
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all rows written before the CTA retires
 }
 

@@ -69,17 +69,26 @@ __global__ void __launch_bounds__(RB) combine_kernel(const double *__restrict__ 
 }
 
 // Ritz vector, its image, residual and Davidson correction in one pass:
-//   x = V s, ax = W s, r = ax - theta x, t = r / (theta - d), rnorm2 += |r|^2
+//   x = V s, ax = W s, r = ax - theta x, t = r / (theta - d)
+//   sums[0] += |r|^2, sums[1] += x . (theta - D)^-1 r, sums[2] += x . (theta - D)^-1 x   (the last two for the Olsen
+//   form of the correction, olsen_kernel)
+__device__ __forceinline__ double davidson_den(double theta, double d) {
+    double den = theta - d;
+    if (fabs(den) < 1.0e-8)
+        den = (den < 0.0) ? -1.0e-8 : 1.0e-8;
+    return den;
+}
+
 __global__ void __launch_bounds__(RB) ritz_residual_kernel(const double *__restrict__ V, const double *__restrict__ W,
                                                            long ld, int k, const double *__restrict__ s, double theta,
                                                            const double *__restrict__ diag, double *__restrict__ x,
                                                            double *__restrict__ ax, double *__restrict__ t, long n,
-                                                           double *__restrict__ rnorm2) {
+                                                           double *__restrict__ sums) {
     extern __shared__ double sh[];
     for (int j = threadIdx.x; j < k; j += RB)
         sh[j] = s[j];
     __syncthreads();
-    double acc = 0.0;
+    double acc[3] = {0.0, 0.0, 0.0};
     for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB) {
         double xv = 0.0, av = 0.0;
         for (int j = 0; j < k; ++j) {
@@ -87,26 +96,38 @@ __global__ void __launch_bounds__(RB) ritz_residual_kernel(const double *__restr
             av = fma(sh[j], W[j * ld + i], av);
         }
         const double r = av - theta * xv;
-        double den = theta - diag[i];
-        if (fabs(den) < 1.0e-8)
-            den = (den < 0.0) ? -1.0e-8 : 1.0e-8;
+        const double den = davidson_den(theta, diag[i]);
         x[i] = xv;
         ax[i] = av;
         t[i] = r / den;
-        acc = fma(r, r, acc);
+        acc[0] = fma(r, r, acc[0]);
+        acc[1] = fma(xv, r / den, acc[1]);
+        acc[2] = fma(xv, xv / den, acc[2]);
     }
-    for (int o = 16; o > 0; o >>= 1)
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ double ws[RB / 32];
-    if ((threadIdx.x & 31) == 0)
-        ws[threadIdx.x >> 5] = acc;
+    __shared__ double ws[3][RB / 32];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double a = acc[q];
+        for (int o = 16; o > 0; o >>= 1)
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0)
+            ws[q][threadIdx.x >> 5] = a;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 3) {
         double a = 0.0;
         for (int q = 0; q < RB / 32; ++q)
-            a += ws[q];
-        atomicAdd(rnorm2, a);
+            a += ws[threadIdx.x][q];
+        atomicAdd(sums + threadIdx.x, a);
     }
+}
+
+// Olsen's correction: t = (theta - D)^-1 (r - eps x) with eps = [x.(theta-D)^-1 r] / [x.(theta-D)^-1 x], i.e. the
+// diagonal-preconditioned residual made orthogonal to the Ritz vector: t -= eps x / (theta - d)
+__global__ void __launch_bounds__(RB) olsen_kernel(double *__restrict__ t, const double *__restrict__ x,
+                                                   const double *__restrict__ diag, double theta, double eps, long n) {
+    for (long i = (long)blockIdx.x * RB + threadIdx.x; i < n; i += (long)gridDim.x * RB)
+        t[i] -= eps * x[i] / davidson_den(theta, diag[i]);
 }
 
 // Thick restart, in place: V_r <- sum_j Z[j][r] V_j for r < kk, vectors V_j = V + j * ld, j < m <= ROT_MAXM.  Every
@@ -329,7 +350,7 @@ struct Solver {
         int err;
         const double *d = stage(s_host, k, &err);
         PYCI_TRY(err);
-        combine_kernel<<<grid, RB, sizeof(double) * k, st>>>(Vb, ld, k, d, alpha, beta, x, nloc);
+        combine_kernel<<<grid, RB, sizeof(double) * (size_t)(k + 2), st>>>(Vb, ld, k, d, alpha, beta, x, nloc);
         ctx->launches++;
         return PYCI_OK;
     }
@@ -406,7 +427,7 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     S.ld = op->npad;
     S.R = R;
     S.grid = (int)std::max<long>(1, std::min<long>((S.nloc + RB - 1) / RB, (long)ctx->sm_count * 8));
-    S.small_cap = std::max(mmax + nroot, 64);
+    S.small_cap = std::max(mmax + 3 * nroot, 64);
     std::memset(&S.stats, 0, sizeof(S.stats));
     const size_t vec = sizeof(double) * (size_t)S.ld;
     PYCI_CUDA(dev_malloc(&S.V, vec * mmax));
@@ -479,6 +500,7 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     std::vector<double> rn(nroot, 0.0);
     std::vector<char> conv(nroot, 0);
     const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+    const bool olsen = !getenv("PYCI_B200_NO_OLSEN");
     // Ritz vectors kept by a restart: half the subspace (PYCI_B200_SOLVER_KEEP overrides; 0 = the wanted ones only)
     int keep_target = std::max(nroot, mmax / 2);
     if (const char *e = getenv("PYCI_B200_SOLVER_KEEP"))
@@ -515,7 +537,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
         tp = now();
         // residuals and corrections
         const int nr = std::min(nroot, m);
-        PYCI_CUDA(cudaMemsetAsync(S.dsmall + S.small_cap - nroot, 0, sizeof(double) * nroot, S.st));
+        double *dsums = S.dsmall + S.small_cap - 3 * nroot; // per root: |r|^2, x.(theta-D)^-1 r, x.(theta-D)^-1 x
+        PYCI_CUDA(cudaMemsetAsync(dsums, 0, sizeof(double) * 3 * nroot, S.st));
         std::vector<double> sj(m);
         for (int r = 0; r < nr; ++r) {
             for (int i = 0; i < m; ++i)
@@ -523,20 +546,20 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             int err;
             const double *dsj = S.stage(sj.data(), m, &err);
             PYCI_TRY(err);
-            ritz_residual_kernel<<<S.grid, RB, sizeof(double) * m, S.st>>>(
+            ritz_residual_kernel<<<S.grid, RB, sizeof(double) * (size_t)(m + 2), S.st>>>(
                 S.V, S.W, S.ld, m, dsj, theta[r], op->diag, S.X + (size_t)r * S.ld, S.AX + (size_t)r * S.ld,
-                S.T + (size_t)r * S.ld, S.nloc, S.dsmall + S.small_cap - nroot + r);
+                S.T + (size_t)r * S.ld, S.nloc, dsums + 3 * r);
             ctx->launches++;
         }
         if (R > 1)
-            PYCI_TRY(comm_allreduce_sum_f64(ctx, S.dsmall + S.small_cap - nroot, nroot));
-        PYCI_CUDA(cudaMemcpyAsync(S.hsmall, S.dsmall + S.small_cap - nroot, sizeof(double) * nroot,
-                                  cudaMemcpyDeviceToHost, S.st));
+            PYCI_TRY(comm_allreduce_sum_f64(ctx, dsums, 3 * nroot));
+        PYCI_CUDA(cudaMemcpyAsync(S.hsmall, dsums, sizeof(double) * 3 * nroot, cudaMemcpyDeviceToHost, S.st));
         PYCI_CUDA(cudaStreamSynchronize(S.st));
+        const std::vector<double> sums(S.hsmall, S.hsmall + 3 * nroot); // (hsmall is reused by the dot products below)
         bool all = (nr == nroot);
         double worst = 0.0;
         for (int r = 0; r < nr; ++r) {
-            rn[r] = std::sqrt(std::max(S.hsmall[r], 0.0));
+            rn[r] = std::sqrt(std::max(sums[3 * r], 0.0));
             conv[r] = rn[r] <= tol * std::max(eps23, std::fabs(theta[r]));
             all = all && conv[r];
             worst = std::max(worst, rn[r]);
@@ -564,8 +587,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             if (keep > nr) {
                 std::memcpy(S.hZ, Z.data(), sizeof(double) * (size_t)m * m);
                 PYCI_CUDA(cudaMemcpyAsync(S.dZ, S.hZ, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, S.st));
-                rotate_kernel<<<S.grid, RB, sizeof(double) * (size_t)m * m, S.st>>>(S.V, S.ld, m, keep, S.dZ, S.nloc);
-                rotate_kernel<<<S.grid, RB, sizeof(double) * (size_t)m * m, S.st>>>(S.W, S.ld, m, keep, S.dZ, S.nloc);
+                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.V, S.ld, m, keep, S.dZ, S.nloc);
+                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.W, S.ld, m, keep, S.dZ, S.nloc);
                 ctx->launches += 2;
                 PYCI_CUDA(cudaStreamSynchronize(S.st)); // hZ is reused by the next restart
             } else {
@@ -584,6 +607,11 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             if (conv[r])
                 continue;
             double *t = S.T + (size_t)r * S.ld;
+            if (olsen && std::fabs(sums[3 * r + 2]) > 1.0e-300) {
+                const double eps = sums[3 * r + 1] / sums[3 * r + 2];
+                olsen_kernel<<<S.grid, RB, 0, S.st>>>(t, S.X + (size_t)r * S.ld, op->diag, theta[r], eps, S.nloc);
+                ctx->launches++;
+            }
             double rel = 0.0;
             PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
             if (rel < 1.0e-10)

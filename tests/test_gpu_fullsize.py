@@ -329,3 +329,25 @@ def test_join_is_chosen_for_config5_style_space(cabi, ctx):
     op.close()
     w.close()
     ham.close()
+
+
+@pytest.mark.parametrize("kind,n,occ,count", [("genci", 14, (5, 0), 1800), ("fullci", 9, (3, 3), 5000)])
+def test_rows_too_long_for_shared_memory_go_through_hbm(monkeypatch, kind, n, occ, count):
+    """Rows longer than the shared-memory row buffer (dominant determinants of a heat-bath space reach 10^4 entries)
+    are built by a second launch with the row buffers in HBM.  PYCI_B200_SHORT_CAP forces that launch for every row of
+    more than 40 entries: same operator, bit for bit, with and without the segment-pair join."""
+    import pyci_b200 as pyci
+    okind = {"genci": O.GENCI, "fullci": O.FULLCI}[kind]
+    dets = _selected(okind, n, occ, count, 8)
+    ecore, one, two = O.synthetic_integrals(n, 19)
+    ham = pyci.hamiltonian(ecore, one, two)
+    oi, ox, od = O.sparse_op(okind, n, occ[0], occ[1], dets, (one, two))
+    assert np.max(np.diff(oi)) > 40
+    monkeypatch.setenv("PYCI_B200_SHORT_CAP", "40")
+    monkeypatch.setenv("PYCI_B200_NO_SORTED_PATH", "1")
+    for join in ("PYCI_B200_FORCE_JOIN", "PYCI_B200_NO_JOIN"):
+        monkeypatch.setenv(join, "1")
+        wfn = getattr(pyci, kind + "_wfn")(n, occ[0], occ[1], dets)
+        op = pyci.sparse_op(ham, wfn)
+        assert np.array_equal(op.indptr(), oi) and np.array_equal(op.indices(), ox) and np.array_equal(op.data(), od), join
+        monkeypatch.delenv(join)
