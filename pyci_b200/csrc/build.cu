@@ -239,7 +239,7 @@ __device__ u64 *block_radix_sort(u64 *a, u64 *b, int m, int passes, int dbits, u
 template<int KIND, int KM, bool LAZY>
 __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> index, u32 nSa, u32 nSb,
                                                    const uint2 *__restrict__ hitlist, int cap, u64 *gscratch,
-                                                   int short_cap) {
+                                                   int short_cap, int staged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: keys A | keys B | values | radix counters | excitation tables | pair table.  Rows of more than
     // `short_cap` entries (a few dominant determinants of a heat-bath space reach 10^4) do not fit shared memory:
@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         const int ndiag = (row < P.ncol) ? 1 : 0; // the diagonal takes slot 0 below
         const int nh = (int)(P.indptr[r + 1] - P.indptr[r]) - ndiag;
         const bool recorded = hitlist != nullptr && nh <= cap; // hits of this row were recorded by the count pass
-        if (KIND != PYCI_DOCI && !recorded)
+        // ... or, when they overflowed the list, staged in the row's place in the CSR arrays by a second join pass
+        const bool staged_row = staged != 0 && !recorded;
+        if (KIND != PYCI_DOCI && !recorded && !staged_row)
             build_tables<KIND, true>(P, rs, T, nSa, nSb);
         if (threadIdx.x == 0 && row < P.ncol) { // diagonal, sparseop.cpp:252-255 / :421-424 / :496-499
             const int slot = atomicAdd(&rs.count, 1);
@@ -285,11 +287,13 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         }
         __syncthreads();
         int nlow = 0;
-        if (recorded) {
+        if (recorded || staged_row) {
             // sparse row recorded by the count pass: evaluate the hits only (no enumeration, no probes, no tables)
             const uint2 *hrow = hitlist + (size_t)r * cap;
+            const long st0 = P.indptr[r] + ndiag;
             for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-                const uint2 h = hrow[k];
+                const uint2 h = recorded ? hrow[k]
+                                         : make_uint2((u32)__double_as_longlong(P.vals[st0 + k]), (u32)P.cols[st0 + k]);
                 const double v = hit_element<KIND>(P, rs, pairs, h.x);
                 const int slot = ndiag + k;
                 keyA[slot] = ((u64)h.y << 32) | (u32)slot;
@@ -697,9 +701,10 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     ctx->launches += 2;
     const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
     PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
-    // PYCI_B200_FILL_V1: the first form of the kernel (every warp passes through every segment) instead of the
-    // warp-specialised one; both write the same bytes
-    const bool v1 = getenv("PYCI_B200_FILL_V1") != nullptr;
+    // PYCI_B200_FILL_WS: the warp-specialised form of the kernel instead of the default one (every warp passes through
+    // every segment); both write the same bytes.  Measured (profiles/r2c): equal at config 3 (5.10 ms both), 11 % slower
+    // at config 4 on one GPU (27.8 vs 25.0 ms) -- the 192 alpha-beta threads make more trips than 256 do.
+    const bool v1 = getenv("PYCI_B200_FILL_WS") == nullptr;
     if (with_slice) {
         auto k = v1 ? fill_complete_kernel<true> : fill_complete_ws_kernel<true>;
         PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
@@ -752,6 +757,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     const bool analytic = wfn->complete && op->ncol == wfn->ndet;
     long nnz = 0;
     int maxrow = 0;
+    bool joined = false; // the stored entries were found by the segment-pair join
     if (analytic) {
         // complete space: every excitation is in the wave function, so each row holds ncand + 1 entries and the row
         // pointer is a multiplication -- no count pass, no scan, nothing to read back
@@ -781,8 +787,13 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 cudaMemGetInfo(&free_b, &total_b);
                 const long budget = (long)(free_b / 4);
                 long c = std::min<long>(1024, std::min<long>((long)P.ncand, budget / (8 * std::max<long>(nloc, 1))));
+                long min_c = std::min<long>(32, (long)P.ncand);
+                if (const char *e = getenv("PYCI_B200_HITCAP")) { // tests: a short list, so that rows overflow it
+                    c = std::max(1L, std::min<long>(c, atol(e)));
+                    min_c = 1;
+                }
                 const bool force_join = getenv("PYCI_B200_FORCE_JOIN") != nullptr;
-                if (!sorted_path && (P.ncand >= 2048 || force_join) && c >= std::min<long>(32, (long)P.ncand) && c > 0 &&
+                if (!sorted_path && (P.ncand >= 2048 || force_join) && c >= min_c && c > 0 &&
                     !getenv("PYCI_B200_NO_HITLIST")) {
                     hitcap = (int)c;
                     PYCI_CUDA(dev_malloc(&hitlist, sizeof(uint2) * (size_t)nloc * (size_t)hitcap));
@@ -791,7 +802,6 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             // Selected two-body space: find the stored entries by joining the determinant list with itself on
             // segment pairs (join.cuh) when that is predicted to take fewer bit tests than the enumeration takes
             // probes (a probe costs ~10 tests); else enumerate and probe.
-            bool joined = false;
             if constexpr (KIND != PYCI_DOCI) {
                 if (hitlist && !getenv("PYCI_B200_NO_JOIN")) {
                     int used = 0;
@@ -951,6 +961,20 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             const size_t smem = smem_for(block, short_cap);
             // most candidates miss (selected space): evaluate elements for hits only
             const bool lazy = !analytic && (double)nnz < 0.25 * (double)nloc * ((double)P.ncand + 1.0);
+            // rows with more hits than the recorded list holds: a second join pass stages their hits in the CSR arrays
+            // (else the fill pass would enumerate and probe every candidate of those rows)
+            int staged = 0;
+            if constexpr (KIND != PYCI_DOCI) {
+                if (joined && maxrow - 1 > hitcap) {
+                    int *cursor = nullptr, used = 0;
+                    PYCI_CUDA(dev_malloc(&cursor, sizeof(int) * (size_t)(nloc + 1)));
+                    PYCI_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)(nloc + 1), st));
+                    const int rcj = join_run<KIND, JOIN_STAGE>(ctx, wfn, P, nullptr, hitcap, cursor, 1.0e300, &used, nullptr);
+                    dev_free(cursor);
+                    PYCI_TRY(rcj);
+                    staged = used;
+                }
+            }
             PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
             fill_timed = true;
             auto launch = [&](auto kern) -> int {
@@ -960,14 +984,15 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 PYCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                kern<<<(unsigned)grid, block, smem, st>>>(Ps, ix, nSa, nSb, hitlist, hitcap, nullptr, short_cap);
+                kern<<<(unsigned)grid, block, smem, st>>>(Ps, ix, nSa, nSb, hitlist, hitcap, nullptr, short_cap, staged);
                 ctx->launches++;
                 if (long_rows) {
                     const size_t smem2 = smem_for(block, 0);
                     PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem2));
                     const long grid2 = std::min<long>(nloc, (long)ctx->sm_count * std::min(std::max(per_sm, 1), 2));
                     PYCI_CUDA(dev_malloc(&long_scratch, sizeof(u64) * 3 * (size_t)full_rows * (size_t)grid2));
-                    kern<<<(unsigned)grid2, block, smem2, st>>>(P, ix, nSa, nSb, hitlist, hitcap, long_scratch, short_cap);
+                    kern<<<(unsigned)grid2, block, smem2, st>>>(P, ix, nSa, nSb, hitlist, hitcap, long_scratch, short_cap,
+                                                                staged);
                     ctx->launches++;
                 }
                 return PYCI_OK;

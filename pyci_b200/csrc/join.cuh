@@ -36,7 +36,7 @@ struct JoinCombo {
     u32 binmask;
 };
 
-enum { JOIN_HITLIST = 0, JOIN_RDM = 1 };
+enum { JOIN_HITLIST = 0, JOIN_RDM = 1, JOIN_STAGE = 2 };
 
 __device__ __forceinline__ u32 join_key(const JoinCombo &C, u64 a, u64 b) {
     u64 x = (a & C.m[0]) * 0x9E3779B97F4A7C15ULL + (b & C.m[1]) * 0xC2B2AE3D27D4EB4FULL;
@@ -232,6 +232,9 @@ __device__ void join_rdm_scatter(const BuildParams &P, u64 A, u64 B, u32 code, d
 // One warp per row; rows are handed out by an atomic counter.  The lanes stride over the row's bucket.
 // JOIN_HITLIST: append (candidate index, column) to hitlist[r][*] (up to cap) and count in rowcnt[r].
 // JOIN_RDM: scatter c_row c_col sign for col > row.
+// JOIN_STAGE: second pass for the rows whose hits overflowed the list (more than cap; the row pointer is known by
+// now): (column, candidate index) go straight into the row's place in the CSR arrays -- cols[] and, as a bit pattern,
+// vals[] -- where the fill pass picks them up, evaluates, sorts and overwrites them; rowcnt[] is a zeroed cursor.
 template<int KIND, int MODE>
 __global__ void __launch_bounds__(256) join_rows_kernel(BuildParams P, JoinCombo C, const long *__restrict__ start,
                                                         const u64 *__restrict__ sdet, const u32 *__restrict__ sidx,
@@ -252,7 +255,13 @@ __global__ void __launch_bounds__(256) join_rows_kernel(BuildParams P, JoinCombo
         const u32 key = join_key(C, A, B);
         const long b0 = start[key], b1 = start[key + 1];
         const int ndiag = (row < P.ncol) ? 1 : 0;
-        int cnt = (MODE == JOIN_HITLIST) ? rowcnt[r] : 0;
+        long stage0 = 0;
+        if (MODE == JOIN_STAGE) {
+            stage0 = P.indptr[r] + ndiag;
+            if (P.indptr[r + 1] - stage0 <= (long)cap)
+                continue; // recorded in full by the first pass
+        }
+        int cnt = (MODE == JOIN_HITLIST || MODE == JOIN_STAGE) ? rowcnt[r] : 0;
         const double ci = (MODE == JOIN_RDM) ? __ldg(P.coeffs + row) : 0.0;
         for (long base = b0; base < b1; base += 32) {
             const long p = base + lane;
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(256) join_rows_kernel(BuildParams P, JoinCombo
                         own = own && (((xa & C.low[q][0]) | (xb & C.low[q][1])) != 0ULL);
                     if (own) {
                         j = __ldg(sidx + p);
-                        hit = (MODE == JOIN_HITLIST) ? ((long)j < P.ncol) : ((long)j > row);
+                        hit = (MODE == JOIN_RDM) ? ((long)j > row) : ((long)j < P.ncol);
                     }
                 }
             }
@@ -291,11 +300,22 @@ __global__ void __launch_bounds__(256) join_rows_kernel(BuildParams P, JoinCombo
                     }
                     cnt += __popc(msk);
                 }
+            } else if (MODE == JOIN_STAGE) {
+                const u32 msk = __ballot_sync(0xffffffffu, hit);
+                if (msk) {
+                    if (hit) {
+                        const long at = stage0 + cnt + __popc(msk & lt);
+                        P.cols[at] = (int)j;
+                        P.vals[at] = __longlong_as_double(
+                            (long long)join_candidate<KIND>(P, A, B, join_pair_code<KIND>(A, B, A2, B2)));
+                    }
+                    cnt += __popc(msk);
+                }
             } else if (hit) {
                 join_rdm_scatter<KIND>(P, A, B, join_pair_code<KIND>(A, B, A2, B2), ci * __ldg(P.coeffs + j));
             }
         }
-        if (MODE == JOIN_HITLIST && lane == 0)
+        if ((MODE == JOIN_HITLIST || MODE == JOIN_STAGE) && lane == 0)
             rowcnt[r] = cnt;
     }
 }
@@ -418,6 +438,8 @@ int join_run(pyci_ctx *ctx, const pyci_wfn *wfn, const BuildParams &P, uint2 *hi
                 combos[nc++] = join_make_combo(plan, s1, s2, (u32)(nbins - 1));
         PYCI_CUDA(dev_malloc(&S.cnt, sizeof(int) * (size_t)nbins));
         // ---- predicted work: sum over segment pairs of the squared bucket sizes, scaled to this rank's rows
+        // (a JOIN_STAGE pass repeats a join that was already chosen: nothing to predict)
+        if (MODE != JOIN_STAGE) {
         PYCI_CUDA(dev_malloc(&S.sumsq, sizeof(double)));
         PYCI_CUDA(cudaMemsetAsync(S.sumsq, 0, sizeof(double), st));
         for (int c = 0; c < nc; ++c) {
@@ -434,6 +456,7 @@ int join_run(pyci_ctx *ctx, const pyci_wfn *wfn, const BuildParams &P, uint2 *hi
             *tests_out = tests;
         if (tests > budget_tests)
             return PYCI_OK;
+        }
         // ---- per segment pair: counting sort of the determinants by bucket, then every row meets its bucket
         PYCI_CUDA(dev_malloc(&S.start, sizeof(long) * (size_t)(nbins + 1)));
         PYCI_CUDA(dev_malloc(&S.cursor, sizeof(unsigned long long) * (size_t)nbins));

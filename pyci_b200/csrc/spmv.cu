@@ -42,11 +42,16 @@ constexpr int SPMV_BLOCK = 256;
 // (row pointer -> values/columns -> x gathers -> reduction).
 __global__ void __launch_bounds__(SPMV_BLOCK, 8)
 spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
-                const double *__restrict__ x, double *__restrict__ y, long nrows) {
+                const double *__restrict__ x, double *__restrict__ y, long nrows, long chunk) {
     const int lane = threadIdx.x & 31;
-    const long warp = ((long)blockIdx.x * SPMV_BLOCK + threadIdx.x) >> 5;
-    const long nwarps = ((long)gridDim.x * SPMV_BLOCK) >> 5;
-    for (long r = warp; r < nrows; r += nwarps) {
+    // chunk > 0: every CTA walks a contiguous range of `chunk` rows, eight (one per warp) at a time -- neighbouring
+    // rows of a selected space gather neighbouring x, so the sectors one batch pulled into L1 serve the next;
+    // chunk == 0: rows dealt round-robin over all warps of the grid
+    const long warp = chunk > 0 ? (long)blockIdx.x * chunk + (threadIdx.x >> 5)
+                                : ((long)blockIdx.x * SPMV_BLOCK + threadIdx.x) >> 5;
+    const long nwarps = chunk > 0 ? (long)(SPMV_BLOCK / 32) : ((long)gridDim.x * SPMV_BLOCK) >> 5;
+    const long rend = chunk > 0 ? min(nrows, ((long)blockIdx.x + 1) * chunk) : nrows;
+    for (long r = warp; r < rend; r += nwarps) {
         const long start = __ldg(indptr + r), end = __ldg(indptr + r + 1);
         double acc0 = 0.0, acc1 = 0.0;
         long p = start;
@@ -445,7 +450,15 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
     if (tpr == 1) {
         const long blocks = (op->nloc * 32 + SPMV_BLOCK - 1) / SPMV_BLOCK;
         const long g = std::min<long>(blocks, (long)ctx->sm_count * op->spmv_ctas);
-        spmv_short_rows<<<(unsigned)g, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc);
+        // PYCI_B200_SPMV_CHUNK=k: contiguous ranges of k rows per CTA (0 = round-robin rows, the default)
+        static const long chunk_env = getenv("PYCI_B200_SPMV_CHUNK") ? atol(getenv("PYCI_B200_SPMV_CHUNK")) : 0;
+        long chunk = 0, gg = g;
+        if (chunk_env > 0) {
+            chunk = (chunk_env + 7) & ~7L;
+            gg = (op->nloc + chunk - 1) / chunk;
+        }
+        spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc,
+                                                                      chunk);
         ctx->launches++;
         PYCI_CUDA(cudaGetLastError());
         return PYCI_OK;

@@ -72,6 +72,26 @@ e2, _ = op2.solve(n=1, tol=1e-9)
 ip2, ix2, dv2 = O.sparse_op(O.FULLCI, n, occ[0], occ[1], sel.to_det_array(), (s1, s2))
 e2o, _ = O.lowest_eigenpair(ip2, ix2, dv2, len(sel))
 assert abs(e2[0] - e2o) < 1e-9, (e2, e2o)
+# ---- selected GenCI space through the segment-pair join (join.cuh), row-sharded: this rank's rows x all determinants
+os.environ["PYCI_B200_FORCE_JOIN"] = "1"
+ng, og = 16, 5
+_, g1, g2 = O.synthetic_integrals(ng, 77)
+alld = O.all_dets(O.GENCI, ng, og)
+gd = np.ascontiguousarray(alld[np.random.default_rng(12).permutation(len(alld))[:3000]])
+gw = pyci.genci_wfn(ng, og, 0, gd)
+gh = pyci.hamiltonian(0.0, g1, g2)
+opg = pyci.sparse_op(gh, gw)
+gi, gx, gv = O.sparse_op(O.GENCI, ng, og, 0, gd, (g1, g2))
+lo, cnt = row_partition(len(gd), len(gd), world)[rank]
+assert np.array_equal(opg.indptr(), gi[lo:lo + cnt + 1] - gi[lo])
+assert np.array_equal(opg.indices(), gx[gi[lo]:gi[lo + cnt]])
+assert np.array_equal(opg.data(), gv[gi[lo]:gi[lo + cnt]])
+cg = seeded_vec(len(gd), 5)
+cg /= np.linalg.norm(cg)
+r1, r2 = pyci.compute_rdms(gw, cg)
+q1, q2 = O.compute_rdms(O.GENCI, ng, og, 0, gd, cg)
+assert np.max(np.abs(r1 - q1)) < 1e-12 and np.max(np.abs(r2 - q2)) < 1e-12
+del os.environ["PYCI_B200_FORCE_JOIN"]
 dist.barrier()
 print("rank %d of %d ok: launches %d" % (rank, world, pyci.launch_count()), flush=True)
 dist.destroy_process_group()

@@ -279,7 +279,12 @@ def test_segment_pair_join_equals_enumeration(monkeypatch, kind, n, occ, count):
     c = seeded_vec(len(dets), 2)
     c /= np.linalg.norm(c)
     res = {}
-    for mode in ("PYCI_B200_FORCE_JOIN", "PYCI_B200_NO_JOIN"):
+    for mode in ("PYCI_B200_FORCE_JOIN", "PYCI_B200_NO_JOIN", "PYCI_B200_FORCE_JOIN+overflow"):
+        if mode.endswith("+overflow"):
+            # a recorded-hit list of 6 entries per row: most rows overflow it, and a second join pass stages their
+            # hits in the CSR arrays (the path rows of > 1024 entries take in a heat-bath space)
+            monkeypatch.setenv("PYCI_B200_HITCAP", "6")
+            mode = "PYCI_B200_FORCE_JOIN"
         monkeypatch.setenv(mode, "1")
         monkeypatch.setenv("PYCI_B200_NO_SORTED_PATH", "1")
         wfn = getattr(pyci, kind + "_wfn")(n, occ[0], occ[1], dets)
@@ -297,6 +302,7 @@ def test_segment_pair_join_equals_enumeration(monkeypatch, kind, n, occ, count):
         np.testing.assert_allclose(r2, o2, rtol=0, atol=1e-13)
         res[mode] = (out, r1, r2)
         monkeypatch.delenv(mode)
+        monkeypatch.delenv("PYCI_B200_HITCAP", raising=False)
 
 
 def test_join_is_chosen_for_config5_style_space(cabi, ctx):

@@ -103,13 +103,13 @@ def test_configs_digest_and_energy(pyci, digests, fn, kind, occ, pinned):
     np.testing.assert_allclose(r2, o2, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("fill", ["warp-specialised", "v1"])
+@pytest.mark.parametrize("fill", ["default", "warp-specialised"])
 @pytest.mark.parametrize("n,occ", [(10, (4, 4)), (9, (4, 3))])
 def test_synthetic_fullci_digest(pyci, digests, monkeypatch, n, occ, fill):
-    """Both forms of the complete-space fill kernel (fill_complete_ws_kernel, and fill_complete_kernel behind
-    PYCI_B200_FILL_V1) against the digests of the compiled reference's operator."""
-    if fill == "v1":
-        monkeypatch.setenv("PYCI_B200_FILL_V1", "1")
+    """Both forms of the complete-space fill kernel (fill_complete_kernel, and fill_complete_ws_kernel behind
+    PYCI_B200_FILL_WS) against the digests of the compiled reference's operator."""
+    if fill == "warp-specialised":
+        monkeypatch.setenv("PYCI_B200_FILL_WS", "1")
     ecore, one, two = O.synthetic_integrals(n, 1234)
     ham = pyci.hamiltonian(ecore, one, two)
     wfn = pyci.fullci_wfn(n, *occ)
