@@ -285,9 +285,9 @@ static int wfn_check_args(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, lo
         PYCI_FAIL(PYCI_ERR_VALUE, "nocc_up != nocc_dn");
     if (kind == PYCI_GENCI && nocc_dn != 0)
         PYCI_FAIL(PYCI_ERR_VALUE, "nocc_dn != 0");
-    if (nbasis > 64)
+    if (nbasis > 256)
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED,
-                  "nbasis = %ld needs multi-word determinants; the device kernels handle nbasis <= 64", nbasis);
+                  "nbasis = %ld: the device kernels handle nbasis <= 64 (fast paths) and <= 256 (multi-word path)", nbasis);
     return ctx_activate(ctx);
 }
 
@@ -299,8 +299,10 @@ static pyci_wfn *wfn_new(pyci_ctx *ctx, int kind, long nbasis, long nocc_up, lon
     wfn->nocc_up = nocc_up;
     wfn->nocc_dn = nocc_dn;
     wfn->ndet = ndet;
-    wfn->nwords = (kind == PYCI_FULLCI) ? 2 : 1;
-    if (kind == PYCI_FULLCI)
+    wfn->nwords = ((kind == PYCI_FULLCI) ? 2 : 1) * (int)((nbasis + 63) / 64); // common.cpp:280-282
+    if (nbasis > 64)
+        wfn->keymode = KEY_MW; // multi-word strings: the generic slow path (multiword.cu)
+    else if (kind == PYCI_FULLCI)
         wfn->keymode = (nbasis <= 16) ? KEY32 : (nbasis <= 32) ? KEY64 : KEY128;
     else
         wfn->keymode = (nbasis <= 32) ? KEY32 : KEY64;
@@ -335,6 +337,8 @@ int pyci_wfn_create_all_dets(pyci_ctx *ctx, int kind, long nbasis, long nocc_up,
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
     *out = nullptr;
     PYCI_TRY(wfn_check_args(ctx, kind, nbasis, nocc_up, nocc_dn));
+    if (nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "determinants of more than 64 orbitals are not generated on the device: upload them");
     const long ndet = full_space_size(kind, nbasis, nocc_up, nocc_dn);
     if (ndet >= (1L << 31) - 1)
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "ndet = %ld out of range for int32 column indices", ndet);
@@ -393,6 +397,9 @@ int pyci_wfn_add_hci(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const do
     if (ham->nbasis != wfn->nbasis)
         PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian has %ld basis functions, wave function %ld", ham->nbasis, wfn->nbasis);
     *n_new = 0;
+    if (wfn->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "add_hci of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     if (wfn->ndet == 0)
         return PYCI_OK;
     PYCI_TRY(ctx_activate(ctx));
@@ -416,6 +423,9 @@ int pyci_compute_enpt2(pyci_ctx *ctx, const pyci_ham *ham, pyci_wfn *wfn, const 
     if (wfn->kind == PYCI_DOCI)
         PYCI_FAIL(PYCI_ERR_VALUE, "compute_enpt2 of a DOCI wave function runs on its FullCI image (enpt2.cpp:376-380): "
                                   "upload the determinants as (d, d) FullCI strings");
+    if (wfn->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "compute_enpt2 of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     PYCI_TRY(ctx_activate(ctx));
     PYCI_TRY(wfn_ensure_index(wfn));
     return enpt2_impl(ctx, ham, wfn, coeffs, energy, eps, out, nterms, &wfn->ext_seconds);
@@ -427,6 +437,9 @@ int pyci_wfn_index_dets(pyci_wfn *wfn, long n, const uint64_t *dets, long *out) 
     if (n <= 0)
         return PYCI_OK;
     pyci_ctx *ctx = wfn->ctx;
+    if (wfn->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "index_det of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     PYCI_TRY(ctx_activate(ctx));
     u64 *d = nullptr;
     long *o = nullptr;
@@ -531,7 +544,7 @@ int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn) {
     if (wfn->ndet < op->nrow)
         PYCI_FAIL(PYCI_ERR_VALUE, "the wave function holds fewer determinants (%ld) than the operator has rows (%ld)",
                   wfn->ndet, op->nrow);
-    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1 || op->foreign)
+    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1 || op->foreign || wfn->nbasis > 64)
         PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "incremental update needs a square symmetric operator on one rank: rebuild instead");
     if (wfn->kind == PYCI_DOCI ? (!ham->h || !ham->v || !ham->w) : (!ham->one_mo || !ham->two_mo))
         PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian lacks the integrals this wave-function kind needs");
@@ -881,6 +894,9 @@ int pyci_op_solve(pyci_op *op, long n, const double *c0, long ncv, long maxiter,
 int pyci_compute_rdms(pyci_ctx *ctx, const pyci_wfn *wfn, const double *coeffs, double *rdm1, double *rdm2) {
     if (!ctx || !wfn || !coeffs || !rdm1 || !rdm2)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (wfn->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "compute_rdms of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     PYCI_TRY(ctx_activate(ctx));
     PYCI_TRY(wfn_ensure_index(wfn));
     return rdms_impl(ctx, wfn, coeffs, rdm1, rdm2);
@@ -890,6 +906,9 @@ int pyci_compute_transition_rdms(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci
                                  const double *coeffs2, double *rdm1, double *rdm2) {
     if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !rdm1 || !rdm2)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (wfn1->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "compute_transition_rdms of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     PYCI_TRY(ctx_activate(ctx));
     PYCI_TRY(wfn_ensure_index(wfn2));
     return trdms_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, rdm1, rdm2);
@@ -899,6 +918,9 @@ int pyci_compute_overlap(pyci_ctx *ctx, const pyci_wfn *wfn1, const pyci_wfn *wf
                          const double *coeffs2, double *out) {
     if (!ctx || !wfn1 || !wfn2 || !coeffs1 || !coeffs2 || !out)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    if (wfn1->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "compute_overlap of wave functions with more than 64 orbitals is not on the device "
+                                        "(multi-word determinants: sparse_op / matvec / solve only)");
     PYCI_TRY(ctx_activate(ctx));
     PYCI_TRY(wfn_ensure_index(wfn2));
     return overlap_impl(ctx, wfn1, wfn2, coeffs1, coeffs2, out);

@@ -33,6 +33,7 @@ __global__ void diag_kernel(BuildParams P) {
 }
 
 constexpr int UNROLL = 4;
+constexpr int RANK_SORT_MAX = 320; // rows up to this many entries are ordered by a rank sort, longer ones by the radix sort
 
 // ---- count pass ---------------------------------------------------------------------------------
 // hitlist != nullptr: the hits of a row (candidate index, column) are also recorded, up to `cap` per row, so that
@@ -350,7 +351,23 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
             atomicAdd(&low_count, nlow);
         __syncthreads();
         const int m = rs.count;
-        const u64 *sorted = block_radix_sort(keyA, keyB, m, P.sort_passes, P.sort_dbits, hist, tot);
+        const u64 *sorted;
+        if (m <= RANK_SORT_MAX) {
+            // short row (the rows of a selected space hold ~10^2 entries): rank sort -- entry e goes to the number of
+            // entries with a smaller key; every thread reads the same key at a time (shared-memory broadcast).  The
+            // radix sort below costs ~10^4 warp instructions per row whatever its length (ncu r2d).
+            for (int e = threadIdx.x; e < m; e += blockDim.x) {
+                const u64 key = keyA[e];
+                int rank = 0;
+                for (int f = 0; f < m; ++f)
+                    rank += keyA[f] < key;
+                keyB[rank] = key;
+            }
+            __syncthreads();
+            sorted = keyB;
+        } else {
+            sorted = block_radix_sort(keyA, keyB, m, P.sort_passes, P.sort_dbits, hist, tot);
+        }
         // stream the row out: columns ascending, values gathered through the slot index
         const long out0 = P.indptr[r];
         for (int e = threadIdx.x; e < m; e += blockDim.x) {
@@ -705,15 +722,17 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     // every segment); both write the same bytes.  Measured (profiles/r2c): equal at config 3 (5.10 ms both), 11 % slower
     // at config 4 on one GPU (27.8 vs 25.0 ms) -- the 192 alpha-beta threads make more trips than 256 do.
     const bool v1 = getenv("PYCI_B200_FILL_WS") == nullptr;
-    if (with_slice) {
-        auto k = v1 ? fill_complete_kernel<true> : fill_complete_ws_kernel<true>;
-        PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
-    } else {
-        auto k = v1 ? fill_complete_kernel<false> : fill_complete_ws_kernel<false>;
-        PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
-    }
+    // PYCI_B200_FILL_STG=0/1: rows leave shared memory by bulk copies (TMA) / by 16-byte st.global of all threads
+    const bool stg = getenv("PYCI_B200_FILL_STG") ? atoi(getenv("PYCI_B200_FILL_STG")) != 0 : false;
+    void (*k)(BuildParams, CompleteParams, int);
+    if (!v1)
+        k = with_slice ? fill_complete_ws_kernel<true> : fill_complete_ws_kernel<false>;
+    else if (stg)
+        k = with_slice ? fill_complete_kernel<true, true> : fill_complete_kernel<false, true>;
+    else
+        k = with_slice ? fill_complete_kernel<true, false> : fill_complete_kernel<false, false>;
+    PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
     ctx->launches++;
     PYCI_CUDA(cudaGetLastError());
@@ -803,7 +822,9 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             // segment pairs (join.cuh) when that is predicted to take fewer bit tests than the enumeration takes
             // probes (a probe costs ~10 tests); else enumerate and probe.
             if constexpr (KIND != PYCI_DOCI) {
-                if (hitlist && !getenv("PYCI_B200_NO_JOIN")) {
+                // (below ~10^4 candidates per row the enumeration finishes before the join's sixty small launches do:
+                // FullCI(16, 4a4b) thinned to 150 000 determinants, 3192 candidates per row: 4.7 ms against 22 ms)
+                if (hitlist && !getenv("PYCI_B200_NO_JOIN") && (P.ncand >= 8192 || getenv("PYCI_B200_FORCE_JOIN"))) {
                     int used = 0;
                     const double budget = getenv("PYCI_B200_FORCE_JOIN") ? 1.0e300 : 10.0 * (double)P.ncand * (double)nloc;
                     PYCI_TRY((join_run<KIND, JOIN_HITLIST>(ctx, wfn, P, hitlist, hitcap, rowcnt, budget, &used, &op->join_tests)));
@@ -936,6 +957,8 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             PYCI_TRY(wfn_ensure_index(wfn));
             ix = make_index<KM>(wfn);
             int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));
+            if (joined) // no row is enumerated by the fill pass: the threads of a CTA only share the row's hits
+                block = pick_block(2 * std::max<long>(1, nnz / std::max<long>(nloc, 1)));
             // keys (ping-pong) + values + radix counters + tables + pair table
             auto smem_for = [&](int blk, long rows) {
                 return (size_t)24 * (size_t)rows + sizeof(u32) * ((size_t)(blk / 32) + 1) * (1u << P.sort_dbits) + tab_bytes +
@@ -1163,6 +1186,8 @@ static int wfn_build_hash(pyci_wfn *wfn) {
 int wfn_ensure_index(const pyci_wfn *wfn) {
     if (wfn->index_valid)
         return PYCI_OK;
+    if (wfn->keymode == KEY_MW)
+        return mw_index_build(const_cast<pyci_wfn *>(wfn));
     return wfn_build_hash(const_cast<pyci_wfn *>(wfn)); // a cache: logically const
 }
 
@@ -1174,6 +1199,11 @@ int wfn_ensure_index(const pyci_wfn *wfn) {
 int wfn_build_index(pyci_wfn *wfn) {
     pyci_ctx *ctx = wfn->ctx;
     PYCI_NVTX("pyci:index(check)");
+    if (wfn->keymode == KEY_MW) { // multi-word strings: index of determinant positions (multiword.cu)
+        wfn->sorted2 = false;
+        wfn->hash_seconds = 0.0;
+        return mw_index_build(wfn);
+    }
     if (wfn->generated && wfn->kind == PYCI_FULLCI && wfn->complete && !getenv("PYCI_B200_EAGER_INDEX")) {
         // unranked on the device in add_all_dets order (pyci_wfn_create_all_dets): sorted, valid and complete by
         // construction -- nothing to check, and the hash index stays deferred (or valid, if something built it)
@@ -1235,6 +1265,10 @@ int wfn_index_dets_impl(pyci_wfn *wfn, long n, const u64 *dets_dev, long *out_de
 }
 
 int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op) {
+    if (wfn->keymode == KEY_MW) {
+        PYCI_TRY(wfn_ensure_index(wfn));
+        return mw_op_build(ctx, ham, wfn, op);
+    }
     BuildParams P;
     PYCI_TRY(enum_params_init(P, wfn));
     const int kind = wfn->kind;

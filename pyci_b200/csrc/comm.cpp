@@ -19,6 +19,10 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     bool ok = false;
     std::string why;
@@ -49,6 +53,10 @@ NcclApi &api() {
         LOAD(CommDestroy)
         LOAD(AllGather)
         LOAD(AllReduce)
+        LOAD(Send)
+        LOAD(Recv)
+        LOAD(GroupStart)
+        LOAD(GroupEnd)
         LOAD(GetErrorString)
 #undef LOAD
         a.ok = true;
@@ -128,14 +136,44 @@ int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count) {
     if (ctx->nranks == 1)
         return PYCI_OK;
     long *d = nullptr;
-    PYCI_CUDA(cudaMalloc(&d, sizeof(long) * count));
-    PYCI_CUDA(cudaMemcpyAsync(d, vals, sizeof(long) * count, cudaMemcpyHostToDevice, ctx->stream));
-    ncclResult_t r = api().AllReduce(d, d, (size_t)count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
-    if (r == ncclSuccess) {
-        cudaMemcpyAsync(vals, d, sizeof(long) * count, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
+    PYCI_CUDA(dev_malloc(&d, sizeof(long) * count)); // stream-ordered pool: no device-wide synchronisation
+    cudaError_t e = cudaMemcpyAsync(d, vals, sizeof(long) * count, cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess)
+        r = api().AllReduce(d, d, (size_t)count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream);
+    if (e == cudaSuccess && r == ncclSuccess) {
+        e = cudaMemcpyAsync(vals, d, sizeof(long) * count, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(ctx->stream);
     }
-    cudaFree(d);
+    dev_free(d);
+    PYCI_CUDA(e);
     PYCI_NCCL(r);
+    return PYCI_OK;
+}
+
+// Personalised exchange of 64-bit words: rank p receives send[soff[p] .. soff[p] + scount[p]) of every rank into
+// recv[roff[q] ..) (q = sender).  One NCCL group of point-to-point sends / receives; the local part is a copy.
+int comm_alltoallv_u64(pyci_ctx *ctx, const unsigned long long *send, const long *scount, const long *soff,
+                       unsigned long long *recv, const long *rcount, const long *roff) {
+    const int R = ctx->nranks, me = ctx->rank;
+    if (scount[me] > 0)
+        PYCI_CUDA(cudaMemcpyAsync(recv + roff[me], send + soff[me], sizeof(unsigned long long) * (size_t)scount[me],
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    if (R == 1)
+        return PYCI_OK;
+    PYCI_NCCL(api().GroupStart());
+    ncclResult_t r = ncclSuccess;
+    for (int p = 0; p < R && r == ncclSuccess; ++p) {
+        if (p == me)
+            continue;
+        if (scount[p] > 0)
+            r = api().Send(send + soff[p], (size_t)scount[p], ncclUint64, p, (ncclComm_t)ctx->comm, ctx->stream);
+        if (r == ncclSuccess && rcount[p] > 0)
+            r = api().Recv(recv + roff[p], (size_t)rcount[p], ncclUint64, p, (ncclComm_t)ctx->comm, ctx->stream);
+    }
+    const ncclResult_t g = api().GroupEnd();
+    PYCI_NCCL(r);
+    PYCI_NCCL(g);
     return PYCI_OK;
 }

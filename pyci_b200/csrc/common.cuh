@@ -82,7 +82,8 @@ struct pyci_ham {
 enum KeyMode {
     KEY32 = 0,  // one u32: one-spin nbasis<=32, or two-spin nbasis<=16 as alpha | beta<<nbasis   ( 8 B slots)
     KEY64 = 1,  // one u64: one-spin nbasis<=64, or two-spin nbasis<=32 as alpha | beta<<nbasis   (16 B slots)
-    KEY128 = 2  // two u64 (alpha, beta): two-spin 32<nbasis<=64                                  (32 B slots)
+    KEY128 = 2, // two u64 (alpha, beta): two-spin 32<nbasis<=64                                  (32 B slots)
+    KEY_MW = 3  // nbasis > 64: slots hold determinant indices, keys are compared in the determinant array (multiword.cu)
 };
 
 struct pyci_wfn {
@@ -155,7 +156,12 @@ void comm_destroy(pyci_ctx *ctx);
 int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, long count_per_rank);
 int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count);
 int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
+int comm_alltoallv_u64(pyci_ctx *ctx, const unsigned long long *send, const long *scount, const long *soff,
+                       unsigned long long *recv, const long *rcount, const long *roff);
 
+// multiword.cu: nbasis > 64
+int mw_index_build(pyci_wfn *wfn);
+int mw_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
 // dets.cu
 int wfn_generate_all_dets(pyci_wfn *wfn, long na, long nb);
 // build.cu

@@ -217,6 +217,36 @@ __global__ void ext_merge_kernel(ExtTable T, const u64 *pay, const u64 *k0, cons
     }
 }
 
+// rank that owns an external determinant: the same rule pt2_reduce_kernel uses for its share
+__device__ __forceinline__ u32 ext_owner(u64 a, u64 b, u32 nranks) { return (ext_home(a, b) >> 7) % nranks; }
+
+template<bool TWO>
+__global__ void owner_count_kernel(const u64 *k0, const u64 *k1, long n, u32 nranks, unsigned long long *cnt) {
+    __shared__ unsigned int h[64];
+    if (threadIdx.x < 64)
+        h[threadIdx.x] = 0;
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        atomicAdd(&h[ext_owner(k0[i], TWO ? k1[i] : 0ULL, nranks)], 1u);
+    __syncthreads();
+    if (threadIdx.x < nranks && h[threadIdx.x])
+        atomicAdd(cnt + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+}
+
+// entries grouped by owner: cursor[p] starts at the first slot of owner p's segment
+template<bool TWO>
+__global__ void owner_scatter_kernel(const u64 *pay, const u64 *k0, const u64 *k1, long n, u32 nranks,
+                                     unsigned long long *cursor, u64 *spay, u64 *s0, u64 *s1) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const u64 a = k0[i], b = TWO ? k1[i] : 0ULL;
+        const unsigned long long at = atomicAdd(cursor + ext_owner(a, b, nranks), 1ULL);
+        spay[at] = pay[i];
+        s0[at] = a;
+        if (TWO)
+            s1[at] = b;
+    }
+}
+
 __global__ void ext_gather_dets_kernel(const u32 *order, const u64 *k0, const u64 *k1, long n, int nwords, u64 *out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -491,9 +521,133 @@ int pack_lists(pyci_ctx *ctx, bool two, const std::vector<ExtList> &lists, long 
     return PYCI_OK;
 }
 
-// The external space of the whole wave function as one duplicate-free list on every rank.  This rank's rows are
-// walked in `split` consecutive chunks (PYCI_B200_EXT_SPLIT, default 1: bounds the size of one table; the chunks'
-// lists are merged like the ranks' lists), then the per-rank lists are all-gathered and merged.
+// Owner-computes merge over ranks: every entry of this rank's list goes to the rank that owns its determinant
+// (hash of the string), which merges what it receives -- duplicates from different ranks combine there (atomicMin /
+// atomicAdd as in the local table).  Each rank ends with the duplicate-free list of the determinants it owns: the merge
+// work is divided by the rank count instead of repeated on every rank.
+template<int MODE>
+int exchange_to_owners(pyci_ctx *ctx, bool two, ExtList &L, ExtList &owned) {
+    const int R = ctx->nranks, me = ctx->rank;
+    cudaStream_t st = ctx->stream;
+    unsigned long long *dcnt = nullptr;
+    u64 *spay = nullptr, *s0 = nullptr, *s1 = nullptr, *rpay = nullptr, *r0 = nullptr, *r1 = nullptr;
+    auto body = [&]() -> int {
+        PYCI_CUDA(dev_malloc(&dcnt, sizeof(unsigned long long) * 2 * (size_t)R));
+        PYCI_CUDA(cudaMemsetAsync(dcnt, 0, sizeof(unsigned long long) * 2 * (size_t)R, st));
+        const unsigned blocks = (unsigned)std::max<long>(1, std::min<long>((L.n + 255) / 256, (long)ctx->sm_count * 8));
+        if (L.n > 0) {
+            if (two)
+                owner_count_kernel<true><<<blocks, 256, 0, st>>>(L.k0, L.k1, L.n, (u32)R, dcnt);
+            else
+                owner_count_kernel<false><<<blocks, 256, 0, st>>>(L.k0, L.k1, L.n, (u32)R, dcnt);
+            ctx->launches++;
+        }
+        std::vector<unsigned long long> hc((size_t)R, 0ULL);
+        PYCI_CUDA(cudaMemcpyAsync(hc.data(), dcnt, sizeof(unsigned long long) * (size_t)R, cudaMemcpyDeviceToHost, st));
+        PYCI_CUDA(cudaStreamSynchronize(st));
+        std::vector<long> scount((size_t)R), soff((size_t)R + 1, 0), rcount((size_t)R), roff((size_t)R + 1, 0);
+        std::vector<unsigned long long> hcur((size_t)R);
+        for (int p = 0; p < R; ++p) {
+            scount[(size_t)p] = (long)hc[(size_t)p];
+            soff[(size_t)p + 1] = soff[(size_t)p] + scount[(size_t)p];
+            hcur[(size_t)p] = (unsigned long long)soff[(size_t)p];
+        }
+        // counts matrix [sender][receiver] summed over ranks (every rank fills its own row)
+        std::vector<long> mat((size_t)R * R, 0);
+        for (int p = 0; p < R; ++p)
+            mat[(size_t)me * R + p] = scount[(size_t)p];
+        PYCI_TRY(comm_allreduce_sum_i64_host(ctx, mat.data(), R * R));
+        for (int q = 0; q < R; ++q) {
+            rcount[(size_t)q] = mat[(size_t)q * R + me];
+            roff[(size_t)q + 1] = roff[(size_t)q] + rcount[(size_t)q];
+        }
+        const long ns = std::max<long>(soff[(size_t)R], 1), nr = std::max<long>(roff[(size_t)R], 1);
+        PYCI_CUDA(dev_malloc(&spay, sizeof(u64) * (size_t)ns));
+        PYCI_CUDA(dev_malloc(&s0, sizeof(u64) * (size_t)ns));
+        if (two)
+            PYCI_CUDA(dev_malloc(&s1, sizeof(u64) * (size_t)ns));
+        PYCI_CUDA(dev_malloc(&rpay, sizeof(u64) * (size_t)nr));
+        PYCI_CUDA(dev_malloc(&r0, sizeof(u64) * (size_t)nr));
+        if (two)
+            PYCI_CUDA(dev_malloc(&r1, sizeof(u64) * (size_t)nr));
+        if (L.n > 0) {
+            PYCI_CUDA(cudaMemcpyAsync(dcnt + R, hcur.data(), sizeof(unsigned long long) * (size_t)R, cudaMemcpyHostToDevice, st));
+            if (two)
+                owner_scatter_kernel<true><<<blocks, 256, 0, st>>>(L.pay, L.k0, L.k1, L.n, (u32)R, dcnt + R, spay, s0, s1);
+            else
+                owner_scatter_kernel<false><<<blocks, 256, 0, st>>>(L.pay, L.k0, L.k1, L.n, (u32)R, dcnt + R, spay, s0, s1);
+            ctx->launches++;
+        }
+        PYCI_TRY(comm_alltoallv_u64(ctx, spay, scount.data(), soff.data(), rpay, rcount.data(), roff.data()));
+        PYCI_TRY(comm_alltoallv_u64(ctx, s0, scount.data(), soff.data(), r0, rcount.data(), roff.data()));
+        if (two)
+            PYCI_TRY(comm_alltoallv_u64(ctx, s1, scount.data(), soff.data(), r1, rcount.data(), roff.data()));
+        PYCI_CUDA(cudaStreamSynchronize(st)); // hcur is read by the copy above
+        const std::vector<long> one(1, roff[(size_t)R]);
+        PYCI_TRY(merge_lists<MODE>(ctx, two, rpay, r0, r1, nr, one, owned));
+        return PYCI_OK;
+    };
+    const int rc = body();
+    dev_free(dcnt);
+    dev_free(spay);
+    dev_free(s0);
+    dev_free(s1);
+    dev_free(rpay);
+    dev_free(r0);
+    dev_free(r1);
+    return rc;
+}
+
+// every rank's owned list, concatenated in rank order, on every rank (the owners' lists are disjoint: no merge)
+int allgather_lists(pyci_ctx *ctx, bool two, ExtList &mine, ExtList &all) {
+    const int R = ctx->nranks;
+    cudaStream_t st = ctx->stream;
+    std::vector<long> rc((size_t)R, 0);
+    rc[(size_t)ctx->rank] = mine.n;
+    PYCI_TRY(comm_allreduce_sum_i64_host(ctx, rc.data(), R));
+    long stride = 1, total = 0;
+    for (long c : rc) {
+        stride = std::max(stride, c);
+        total += c;
+    }
+    u64 *sp = nullptr, *s0 = nullptr, *s1 = nullptr, *g = nullptr;
+    auto body = [&]() -> int {
+        std::vector<ExtList> one(1, mine);
+        PYCI_TRY(pack_lists(ctx, two, one, stride, &sp, &s0, &s1)); // padded to the common stride
+        PYCI_CUDA(dev_malloc(&g, sizeof(u64) * (size_t)stride * (size_t)R));
+        const size_t ob = sizeof(u64) * (size_t)std::max<long>(total, 1);
+        PYCI_CUDA(dev_malloc(&all.pay, ob));
+        PYCI_CUDA(dev_malloc(&all.k0, ob));
+        if (two)
+            PYCI_CUDA(dev_malloc(&all.k1, ob));
+        all.n = total;
+        u64 *src[3] = {sp, s0, s1}, *dst[3] = {all.pay, all.k0, all.k1};
+        for (int a = 0; a < (two ? 3 : 2); ++a) {
+            PYCI_TRY(comm_allgather_f64(ctx, (const double *)src[a], (double *)g, stride)); // bit patterns: no arithmetic
+            long off = 0;
+            for (int p = 0; p < R; ++p) {
+                if (rc[(size_t)p] > 0)
+                    PYCI_CUDA(cudaMemcpyAsync(dst[a] + off, g + (size_t)p * stride, sizeof(u64) * (size_t)rc[(size_t)p],
+                                              cudaMemcpyDeviceToDevice, st));
+                off += rc[(size_t)p];
+            }
+        }
+        return PYCI_OK;
+    };
+    const int rcode = body();
+    dev_free(sp);
+    dev_free(s0);
+    dev_free(s1);
+    dev_free(g);
+    if (rcode != PYCI_OK)
+        all.release();
+    return rcode;
+}
+
+// The external space of the whole wave function as a duplicate-free list: on every rank for add_hci; for ENPT2, when
+// row-sharded, each rank gets the determinants it OWNS (hash of the string mod ranks -- the share pt2_reduce_kernel
+// reduces).  This rank's rows are walked in `split` consecutive chunks (PYCI_B200_EXT_SPLIT, default 1: bounds the size
+// of one table; the chunks' lists are merged locally), then the per-rank lists are exchanged to their owners.
 template<int MODE>
 int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const double *coeffs_dev, double eps,
                      ExtList &out, double *seconds) {
@@ -556,27 +710,19 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
             sp = s0 = s1 = nullptr;
         }
         if (R > 1) {
-            std::vector<long> rcounts((size_t)R, 0);
-            rcounts[(size_t)ctx->rank] = L.n;
-            PYCI_TRY(comm_allreduce_sum_i64_host(ctx, rcounts.data(), (int)R));
-            long rstride = 1;
-            for (long c : rcounts)
-                rstride = std::max(rstride, c);
-            std::vector<ExtList> mine(1, L);
-            PYCI_TRY(pack_lists(ctx, two, mine, rstride, &sp, &s0, &s1)); // send buffers padded to the common stride
-            const size_t gb = sizeof(u64) * (size_t)rstride * (size_t)R;
-            PYCI_CUDA(dev_malloc(&gp, gb));
-            PYCI_CUDA(dev_malloc(&g0, gb));
-            PYCI_TRY(comm_allgather_f64(ctx, (const double *)sp, (double *)gp, rstride)); // bit patterns: no arithmetic
-            PYCI_TRY(comm_allgather_f64(ctx, (const double *)s0, (double *)g0, rstride));
-            if (two) {
-                PYCI_CUDA(dev_malloc(&g1, gb));
-                PYCI_TRY(comm_allgather_f64(ctx, (const double *)s1, (double *)g1, rstride));
-            }
-            ExtList G;
-            PYCI_TRY(merge_lists<MODE>(ctx, two, gp, g0, g1, rstride, rcounts, G));
+            // owner-computes: duplicates found by different ranks meet at the determinant's owner.  ENPT2 stops there
+            // (each rank reduces the determinants it owns); add_hci needs the whole list everywhere: the owners'
+            // duplicate-free lists are all-gathered and concatenated.
+            ExtList owned;
+            PYCI_TRY(exchange_to_owners<MODE>(ctx, two, L, owned));
             L.release();
-            L = G;
+            if (MODE == MODE_PT2) {
+                L = owned;
+            } else {
+                const int rcg = allgather_lists(ctx, two, owned, L);
+                owned.release();
+                PYCI_TRY(rcg);
+            }
         }
         return PYCI_OK;
     };
@@ -706,8 +852,11 @@ int enpt2_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, const do
         PYCI_CUDA(cudaMemcpyAsync(&corr, acc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
         *out = energy + corr;
-        if (nterms)
-            *nterms = L.n;
+        if (nterms) { // row-sharded: L holds the determinants this rank owns
+            long tot = L.n;
+            PYCI_TRY(comm_allreduce_sum_i64_host(ctx, &tot, 1));
+            *nterms = tot;
+        }
         return PYCI_OK;
     };
     int rc = body();

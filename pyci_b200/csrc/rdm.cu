@@ -196,7 +196,7 @@ int run_rdm(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P) {
     // probe per candidate excitation; the enumeration kernel then only adds the diagonal terms.
     if constexpr (KIND != PYCI_DOCI) {
         const bool force = getenv("PYCI_B200_FORCE_JOIN") != nullptr;
-        if (!wfn->complete && (P.ncand >= 2048 || force) && !getenv("PYCI_B200_NO_JOIN")) {
+        if (!wfn->complete && (P.ncand >= 8192 || force) && !getenv("PYCI_B200_NO_JOIN")) {
             int used = 0;
             const double budget = force ? 1.0e300 : 10.0 * (double)P.ncand * (double)P.nloc;
             PYCI_TRY((join_run<KIND, JOIN_RDM>(ctx, wfn, P, nullptr, 0, nullptr, budget, &used, nullptr)));

@@ -293,8 +293,11 @@ def test_unsupported_and_invalid_inputs_fail_loudly(pyci):
     ham = pyci.hamiltonian(ecore, one, two)
     wfn = pyci.doci_wfn(66, 2, 2)
     wfn.add_all_dets()
-    with pytest.raises(RuntimeError):        # nbasis > 64: no device path and no CPU fallback
-        pyci.sparse_op(ham, wfn)
+    with pytest.raises(RuntimeError):        # nbasis > 64: construction / SpMV / solve only (multiword.cu)
+        pyci.compute_rdms(wfn, np.ones(len(wfn)) / np.sqrt(len(wfn)))
+    with pytest.raises(RuntimeError):
+        pyci.add_hci(pyci.hamiltonian(*O.synthetic_integrals(66, 7)), pyci.genci_wfn(66, 3, 0, np.array([[7, 0]], dtype=np.uint64)),
+                     np.ones(1), eps=1e-3)
     ham = pyci.hamiltonian(datafile("h4_sto3g"))
     dets = np.array([[3, 3], [3, 3]], dtype=np.uint64)  # duplicate determinant
     with pytest.raises(ValueError):
@@ -733,3 +736,53 @@ def test_config3_full_size_properties(pyci):
     r1, r2 = pyci.spinize_rdms(d1, d2)
     energy = ecore + np.einsum("ij,ij", h2, r1) + 0.25 * (np.einsum("ijkl,ijkl", g2, r2) - np.einsum("ijlk,ijkl", g2, r2))
     assert abs(energy - es[0]) <= 1e-9
+
+
+@pytest.mark.parametrize("kind,n,occ,count", [("doci", 66, (2, 2), None), ("doci", 130, (3, 3), 4000),
+                                              ("genci", 70, (3, 0), 5000), ("fullci", 65, (2, 1), 6000),
+                                              ("fullci", 129, (2, 2), 3000)])
+def test_multiword_determinants(pyci, kind, n, occ, count):
+    """nbasis > 64 (nword = 2 or 3; the reference builds these, common.cpp:280-282, and its wave-function tests use 65
+    and 129 orbitals, pyci/test/test_wavefunction.py:45): the generic multi-word construction against the oracle --
+    complete and selected spaces, symmetric / non-symmetric / rectangular, product and lowest eigenvalue."""
+    okind = KIND[kind]
+    ecore, one, two = O.synthetic_integrals(n, 13)
+    ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
+    ham = pyci.hamiltonian(ecore, one, two)
+    if count is None:
+        wfn = getattr(pyci, kind + "_wfn")(n, *occ)
+        wfn.add_all_dets()
+        dets = wfn.to_det_array()
+        assert np.array_equal(dets, O.all_dets(okind, n, *occ))
+    else:
+        # a selected space: seeded random occupations (distinct), through the occupation-array constructor
+        rng = np.random.default_rng(3)
+        seen, occs = set(), []
+        while len(occs) < count:
+            a = tuple(sorted(rng.choice(n, occ[0], replace=False)))
+            b = tuple(sorted(rng.choice(n, occ[1], replace=False))) if kind == "fullci" else ()
+            if (a, b) not in seen:
+                seen.add((a, b))
+                if kind == "fullci":
+                    row = np.zeros((2, occ[0]), dtype=np.int64)
+                    row[0] = a
+                    row[1, :occ[1]] = b
+                    occs.append(row)
+                else:
+                    occs.append(np.array(a, dtype=np.int64))
+        wfn = getattr(pyci, kind + "_wfn")(n, occ[0], occ[1], np.ascontiguousarray(np.array(occs)))
+        dets = wfn.to_det_array()
+    assert dets.shape[-1] == (n + 63) // 64
+    for kw in (dict(), dict(symmetric=False), dict(nrow=len(dets) - 3, ncol=len(dets) - 5, symmetric=False)):
+        op = pyci.sparse_op(ham, wfn, **kw)
+        oi, ox, od = O.sparse_op(okind, n, occ[0], occ[1], dets, ints, **kw)
+        assert np.array_equal(op.indptr(), oi) and np.array_equal(op.indices(), ox), kw
+        assert np.array_equal(op.data(), od), kw
+        x = seeded_vec(op.shape[1], 5)
+        yo = O.matvec(oi, ox, od, x, kw.get("symmetric", True))
+        np.testing.assert_allclose(op(x), yo, rtol=0, atol=1e-12 * max(1.0, np.abs(yo).max()))
+    op = pyci.sparse_op(ham, wfn)
+    es, cs = op.solve(n=1, tol=1e-10)
+    oi, ox, od = O.sparse_op(okind, n, occ[0], occ[1], dets, ints)
+    e0, _ = O.lowest_eigenpair(oi, ox, od, len(dets))
+    assert abs(es[0] - (e0 + ecore)) <= E_ATOL
