@@ -722,15 +722,11 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     // every segment); both write the same bytes.  Measured (profiles/r2c): equal at config 3 (5.10 ms both), 11 % slower
     // at config 4 on one GPU (27.8 vs 25.0 ms) -- the 192 alpha-beta threads make more trips than 256 do.
     const bool v1 = getenv("PYCI_B200_FILL_WS") == nullptr;
-    // PYCI_B200_FILL_STG=0/1: rows leave shared memory by bulk copies (TMA) / by 16-byte st.global of all threads
-    const bool stg = getenv("PYCI_B200_FILL_STG") ? atoi(getenv("PYCI_B200_FILL_STG")) != 0 : false;
     void (*k)(BuildParams, CompleteParams, int);
     if (!v1)
         k = with_slice ? fill_complete_ws_kernel<true> : fill_complete_ws_kernel<false>;
-    else if (stg)
-        k = with_slice ? fill_complete_kernel<true, true> : fill_complete_kernel<false, true>;
     else
-        k = with_slice ? fill_complete_kernel<true, false> : fill_complete_kernel<false, false>;
+        k = with_slice ? fill_complete_kernel<true> : fill_complete_kernel<false>;
     PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
@@ -805,7 +801,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
                 const long budget = (long)(free_b / 4);
-                long c = std::min<long>(1024, std::min<long>((long)P.ncand, budget / (8 * std::max<long>(nloc, 1))));
+                long c = std::min<long>(4096, std::min<long>((long)P.ncand, budget / (8 * std::max<long>(nloc, 1))));
                 long min_c = std::min<long>(32, (long)P.ncand);
                 if (const char *e = getenv("PYCI_B200_HITCAP")) { // tests: a short list, so that rows overflow it
                     c = std::max(1L, std::min<long>(c, atol(e)));

@@ -236,9 +236,10 @@ __device__ __forceinline__ void bar_full_arrive(int group) {
 // | the A' = A group | alpha-alpha doubles | alpha singles | beta singles + diagonal) so that the lanes of a
 // warp run the same code, then streams the finished row to HBM with aligned 16-byte stores (scalar 4- and
 // 8-byte stores to rows that start at arbitrary offsets reach only a third of the HBM write bandwidth).
-// STG: the finished row leaves shared memory through 16-byte st.global issued by all 256 threads of the group instead
-// of two bulk copies issued by one thread (tools/write_bw.cu on this row layout: 6.19 TB/s against 5.85 TB/s).
-template<bool SLICE, bool STG>
+// (Measured and dropped, profiles/r2e: letting all 256 threads of the group copy the finished row out with 16-byte
+// st.global -- the faster of the two in the bare store probe tools/write_bw.cu, 6.19 against 5.85 TB/s -- costs a
+// second full barrier per row and the copy on every warp's critical path: 7.29 ms against 5.09 ms with the bulk copies.)
+template<bool SLICE>
 __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             double *bval = sval + ov;
             int *bcol = scol + oc;
             // the bulk stores of the previous row must have read the buffer before it is overwritten
-            if (!STG && t < 32) {
+            if (t < 32) {
                 if (t == 0)
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
@@ -449,33 +450,6 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             }
             // ---- the finished row goes out as two bulk copies (TMA): 16-byte aligned bodies of the value and
             // column streams; the few entries before / after the aligned bodies by scalar stores
-            if (STG) {
-                // every thread of the group copies its share of the finished row: aligned 16-byte bodies of the value
-                // and column streams; the few entries before / after them by scalar stores.  (The loads of this copy
-                // are complete when a thread reaches the next row's FREE barrier: its stores consumed them.)
-                bar_full_sync(group);
-                const u32 hv = ov, nv = (M - hv) >> 1;
-                const u32 hc = min(M, (4u - oc) & 3u), nc = (M - hc) >> 2;
-                double2 *gv = reinterpret_cast<double2 *>(P.vals + out0 + hv);
-                const double2 *sv = reinterpret_cast<const double2 *>(bval + hv);
-                for (u32 i = t; i < nv; i += 256)
-                    gv[i] = sv[i];
-                int4 *gc = reinterpret_cast<int4 *>(P.cols + out0 + hc);
-                const int4 *sc = reinterpret_cast<const int4 *>(bcol + hc);
-                for (u32 i = t; i < nc; i += 256)
-                    gc[i] = sc[i];
-                if (t >= 4 && t < 4 + hv)
-                    P.vals[out0 + t - 4] = bval[t - 4];
-                if (t >= 8 && t < 32 && t - 8 + hv + 2 * nv < M)
-                    P.vals[out0 + hv + 2 * nv + t - 8] = bval[hv + 2 * nv + t - 8];
-                if (t >= 12 && t < 32 && t - 12 < hc)
-                    P.cols[out0 + t - 12] = bcol[t - 12];
-                if (t >= 16 && t < 20 && t - 16 + hc + 4 * nc < M)
-                    P.cols[out0 + hc + 4 * nc + t - 16] = bcol[hc + 4 * nc + t - 16];
-                if (t == 20)
-                    P.lowcnt[r] = (int)(self_off + __ldg(C.B.selfj + rb)) + 1;
-                continue;
-            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (t >= 32) {
                 bar_full_arrive(group);
@@ -508,7 +482,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             }
         }
     }
-    if (!STG && (threadIdx.x & 255u) == 0)
+    if ((threadIdx.x & 255u) == 0)
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all rows written before the CTA retires
 }
 

@@ -17,7 +17,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
+        "l1tex__m_xbar2l1tex_read_bytes.sum"]
 
 
 def launches(tag, lines):
@@ -42,8 +43,28 @@ def launches(tag, lines):
     lines.append("")
 
 
-def full(tag, lines):
-    rep = os.path.join(OUT, tag + "_full.ncu-rep")
+def stalls(rep, kernel_regex):
+    """warp-stall shares of one kernel from the source page (sampling)"""
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name",
+                          "regex:" + kernel_regex], capture_output=True, text=True).stdout
+    hdr, tot = None, collections.Counter()
+    for r in csv.reader(src.splitlines()):
+        if len(r) > 3 and r[0] == "Address":
+            hdr = r
+            cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+            continue
+        if hdr and r and r[0].startswith("0x"):
+            for i in cols:
+                try:
+                    tot[hdr[i]] += int(r[i])
+                except (ValueError, IndexError):
+                    pass
+    n = sum(tot.values()) or 1
+    return ", ".join("%s %.0f%%" % (k.replace("stall_", ""), 100.0 * v / n) for k, v in tot.most_common(6))
+
+
+def full(tag, lines, suffix="_full"):
+    rep = os.path.join(OUT, tag + suffix + ".ncu-rep")
     if not os.path.exists(rep):
         return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -51,7 +72,7 @@ def full(tag, lines):
     if len(rows) < 3:
         return
     hdr, units = rows[0], rows[1]
-    lines.append("## `ncu --set full --clock-control none` of the hot kernels (per launch)\n")
+    lines.append("## `ncu --set full --clock-control none` (%s%s.ncu-rep, per launch)\n" % (tag, suffix))
     seen = set()
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
@@ -64,6 +85,7 @@ def full(tag, lines):
             if k in hdr:
                 i = hdr.index(k)
                 lines.append("| %s | %s | %s |" % (k, r[i], units[i]))
+        lines.append("| warp stall samples | %s | |" % stalls(rep, name.split("<")[0]))
         lines.append("")
 
 
@@ -82,7 +104,14 @@ def main():
     if os.path.exists(g):
         lines.append("## Box\n\n```\n%s```\n" % open(g).read())
     launches(tag, lines)
-    full(tag, lines)
+    for suffix in ("_full", "_join", "_fillsel", "_spmvshort"):
+        full(tag, lines, suffix)
+    for suffix, title in (("_write_bw.log", "tools/write_bw.cu: write bandwidth of the CSR row layout (1 002 001 rows x 2221 entries)"),
+                          ("_spmv_chunk.log", "tools/spmv_chunk.py: short-row SpMV, rows per CTA range (PYCI_B200_SPMV_CHUNK)"),
+                          ("_hci_grow.json", "tools/hci_grow.py: config-5-style space grown by add_hci on the device")):
+        p = os.path.join(OUT, tag + suffix)
+        if os.path.exists(p):
+            lines.append("## %s\n\n```\n%s\n```\n" % (title, open(p).read().strip()))
     with open(os.path.join(PROF, tag + "_summary.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
     src = os.path.join(OUT, tag + "_launches.csv")
