@@ -728,6 +728,11 @@ def run_b200(args, spec, rank, world, local):
     B.barrier()
     note("selected-CI leg")
     sel = selected_ci_leg(cabi, B.ctx, rank, world, not args.no_cpu_baseline, spec["kind"] == "genci")
+    if not args.no_extras:
+        try:
+            sel["large"] = selected_ci_big_leg(cabi, B.ctx)
+        except Exception as exc:  # an extra leg must not take the headline line down; it is reported
+            sel["large"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---- end to end through the public API, host objects in, row pointer out
     d2h_bytes = 0
@@ -829,6 +834,32 @@ def run_b200(args, spec, rank, world, local):
 
 
 HCI_N, HCI_OCC, HCI_STRIDE, HCI_EPS, HCI_EPS_UPDATE = 16, (4, 4), 33, 2.0e-4, 2.0e-2
+HCI_BIG_N, HCI_BIG_STRIDE = 18, 3  # every 3rd determinant of FullCI(18, 4a4b): 3.1 M determinants, 1.4e10 candidates
+
+
+def selected_ci_big_leg(cabi, ctx):
+    """add_hci / compute_enpt2 on a case big enough to divide over 8 GPUs (3.1 M determinants): device seconds of walk +
+    exchange to the owning ranks + merge, the same case at every rank count."""
+    syn = _synthetic()
+    _, one, two = syn.synthetic_integrals(HCI_BIG_N, SEED)
+    full = cabi.Wfn(ctx, cabi.FULLCI, HCI_BIG_N, *HCI_OCC)  # generated on the device
+    dets = np.ascontiguousarray(full.download_dets()[::HCI_BIG_STRIDE])
+    full.close()
+    c = np.random.default_rng(1).standard_normal(len(dets))
+    c /= np.linalg.norm(c)
+    ham = cabi.Ham(ctx, HCI_BIG_N, 0.0, one, two)
+    out = {"workload": "FullCI(%d, %da%db), every %drd determinant, eps %g" % (HCI_BIG_N, HCI_OCC[0], HCI_OCC[1], HCI_BIG_STRIDE, HCI_EPS),
+           "ndet": int(len(dets))}
+    for rep in range(2):  # second pass: warm allocations
+        wfn = cabi.Wfn(ctx, cabi.FULLCI, HCI_BIG_N, HCI_OCC[0], HCI_OCC[1], dets)
+        pt, nt = wfn.compute_enpt2(ham, c, -10.0, HCI_EPS)
+        out["enpt2_seconds_device"], out["external_determinants"], out["enpt2"] = wfn.ext_seconds(), int(nt), pt
+        new = wfn.add_hci(ham, c, HCI_EPS)
+        out["add_hci_seconds_device"], out["added"] = wfn.ext_seconds(), int(len(new))
+        wfn.close()
+    ham.close()
+    return out
+
 
 
 def selected_ci_leg(cabi, ctx, rank, world, with_cpu, genci_ref):

@@ -61,6 +61,11 @@ PYCI_API int pyci_device_count(void);
 PYCI_API int pyci_ctx_create(int device, void *stream, pyci_ctx **out);
 PYCI_API void pyci_ctx_destroy(pyci_ctx *ctx);
 PYCI_API int pyci_ctx_synchronize(pyci_ctx *ctx);
+/* Device allocations come from the device's stream-ordered memory pool, whose release threshold the library raises so
+ * that a rebuilt operator reuses the blocks of the destroyed one (10-100 GB) instead of paying the driver again.
+ * Memory the pool holds is invisible to other allocators of the process (torch's caching allocator, cudaMalloc):
+ * this hands everything that is not in use back to the driver. */
+PYCI_API int pyci_ctx_release_memory(pyci_ctx *ctx);
 /* Row-sharding across `nranks` processes (one per GPU of one box).  unique_id: the 128 bytes of an
  * ncclUniqueId made by pyci_nccl_unique_id() on rank 0 and handed to the other ranks by the caller
  * (torch.distributed broadcast, MPI, a file ...).  Collective: every rank must call it. */

@@ -31,7 +31,7 @@ from pyci_b200._pyci import doci_wfn, fullci_wfn, genci_wfn, sparse_op
 from pyci_b200._pyci import get_num_threads, set_num_threads, popcnt, ctz
 from pyci_b200._pyci import compute_rdms, add_hci, compute_enpt2, compute_transition_rdms, compute_overlap
 from pyci_b200._pyci import device_count, set_device, nccl_unique_id, init_comm
-from pyci_b200._pyci import launch_count, reset_launch_count, synchronize
+from pyci_b200._pyci import launch_count, reset_launch_count, synchronize, release_memory
 
 from pyci_b200.utility import make_senzero_integrals, reduce_senzero_integrals, spinize_rdms
 from pyci_b200.utility import add_excitations
@@ -46,5 +46,5 @@ __all__ = [
     "get_num_threads", "set_num_threads", "popcnt", "ctz", "compute_rdms", "add_hci", "compute_enpt2", "compute_transition_rdms", "compute_overlap",
     "make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations",
     "device_count", "set_device", "nccl_unique_id", "init_comm", "launch_count", "reset_launch_count",
-    "synchronize",
+    "synchronize", "release_memory",
 ]

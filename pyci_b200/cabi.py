@@ -35,6 +35,7 @@ PROTOTYPES = {
     "pyci_ctx_create": (_i, [_i, _vp, _vpp]),
     "pyci_ctx_destroy": (None, [_vp]),
     "pyci_ctx_synchronize": (_i, [_vp]),
+    "pyci_ctx_release_memory": (_i, [_vp]),
     "pyci_nccl_unique_id": (_i, [_vp]),
     "pyci_ctx_init_comm": (_i, [_vp, _i, _i, _vp]),
     "pyci_ctx_rank": (_i, [_vp]),
@@ -134,6 +135,10 @@ class Context:
 
     def synchronize(self):
         check(lib().pyci_ctx_synchronize(self.handle))
+
+    def release_memory(self):
+        """hand the pool's unused blocks back to the driver (they are invisible to torch's allocator otherwise)"""
+        check(lib().pyci_ctx_release_memory(self.handle))
 
     def init_comm(self, rank, nranks, unique_id):
         buf = ctypes.create_string_buffer(bytes(unique_id), 128) if nranks > 1 else None

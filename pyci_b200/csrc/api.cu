@@ -186,6 +186,17 @@ int pyci_ctx_synchronize(pyci_ctx *ctx) {
     return PYCI_OK;
 }
 
+int pyci_ctx_release_memory(pyci_ctx *ctx) {
+    if (!ctx)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    PYCI_TRY(ctx_activate(ctx));
+    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool = nullptr;
+    PYCI_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    PYCI_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return PYCI_OK;
+}
+
 int pyci_nccl_unique_id(void *unique_id_128) { return comm_unique_id(unique_id_128); }
 
 int pyci_ctx_init_comm(pyci_ctx *ctx, int rank, int nranks, const void *unique_id_128) {

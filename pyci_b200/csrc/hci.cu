@@ -709,6 +709,9 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
             dev_free(s1);
             sp = s0 = s1 = nullptr;
         }
+        return PYCI_OK;
+    };
+    auto exchange = [&]() -> int {
         if (R > 1) {
             // owner-computes: duplicates found by different ranks meet at the determinant's owner.  ENPT2 stops there
             // (each rank reduces the determinants it owns); add_hci needs the whole list everywhere: the owners'
@@ -726,7 +729,21 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
         }
         return PYCI_OK;
     };
-    const int rc = body();
+    int rc = body();
+    if (R > 1) {
+        // a rank-local failure of the walk (table growth out of memory, ...) must not leave the other ranks waiting
+        // in the exchange: agree on the status first, every rank fails together
+        long bad = rc != PYCI_OK;
+        const int rca = comm_allreduce_sum_i64_host(ctx, &bad, 1);
+        if (rc == PYCI_OK && rca != PYCI_OK)
+            rc = rca;
+        if (rc == PYCI_OK && bad) {
+            pyci_set_error("another rank failed while walking its rows of the external space");
+            rc = PYCI_ERR_RUNTIME;
+        }
+    }
+    if (rc == PYCI_OK)
+        rc = exchange();
     for (ExtList &q : parts)
         q.release();
     dev_free(gp);

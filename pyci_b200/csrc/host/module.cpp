@@ -220,6 +220,8 @@ PYBIND11_MODULE(_pyci, m) {
     m.def("launch_count", []() { return pyci_ctx_launch_count(device_context()); });
     m.def("reset_launch_count", []() { pyci_ctx_reset_launch_count(device_context()); });
     m.def("synchronize", []() { check(pyci_ctx_synchronize(device_context())); });
+    m.def("release_memory", []() { check(pyci_ctx_release_memory(device_context())); },
+          "Return the device memory the library's pool holds but does not use to the driver.");
 
     const char *env = std::getenv("PYCI_NUM_THREADS");
     if (env)

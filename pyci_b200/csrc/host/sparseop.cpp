@@ -4,6 +4,7 @@
 // (rdm.cpp:1011-1055).  All numerical work happens in libpyci_b200.so on the GPU.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "pyci_host.h"
 
@@ -70,11 +71,15 @@ pyci_ctx *device_context() {
 }
 
 void set_device_context(int device, uintptr_t stream) {
-    if (g_ctx) {
-        pyci_ctx_destroy(g_ctx);
-        g_ctx = nullptr;
-    }
-    check(pyci_ctx_create(device, reinterpret_cast<void *>(stream), &g_ctx));
+    // sparse_op objects built so far keep a pointer to the context they were built on (their kernels, frees and
+    // destructors run there): a replaced context is retired, not destroyed -- a few hundred bytes and one stream per
+    // set_device() call, against a use-after-free in every live operator
+    static std::vector<pyci_ctx *> retired;
+    pyci_ctx *fresh = nullptr;
+    check(pyci_ctx_create(device, reinterpret_cast<void *>(stream), &fresh));
+    if (g_ctx)
+        retired.push_back(g_ctx);
+    g_ctx = fresh;
 }
 
 SparseOp::SparseOp(const SQuantOp &ham, const Wfn &wfn, long rows, long cols, bool symm)
