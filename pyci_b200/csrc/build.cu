@@ -690,17 +690,7 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     if (!groups || S.La > 65535u || S.Lb > 65535u || P.n * P.n >= 4096 || S.M >= (1u << 30) ||
         table_bytes > ((size_t)4 << 30) || (long)tsmem > (long)ctx->smem_optin)
         return PYCI_OK; // the general sorted path takes it
-    size_t fsmem = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice).total;
-    // prefetch buffers for the beta-side data of the next row (two per group) when they fit beside the same number of
-    // groups; PYCI_B200_FILL_PF=0/1 forces them off / on (on: with fewer groups if need be)
-    bool pf = false;
-    {
-        const char *e = getenv("PYCI_B200_FILL_PF");
-        const size_t with_pf = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice, S.Lb, L1b, (u32)P.nocc_b).total;
-        pf = (e ? atoi(e) != 0 : true) && (long)with_pf <= (long)ctx->smem_optin && !getenv("PYCI_B200_FILL_WS");
-        if (pf)
-            fsmem = with_pf;
-    }
+    const size_t fsmem = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice).total;
     CompleteParams C;
     memset(&C, 0, sizeof(C));
     int rc = alloc_string_tables(C.A, Na, S.La, L1a, (u32)P.nocc_a, P.nSa, P.nDa);
@@ -735,10 +725,8 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     void (*k)(BuildParams, CompleteParams, int);
     if (!v1)
         k = with_slice ? fill_complete_ws_kernel<true> : fill_complete_ws_kernel<false>;
-    else if (pf)
-        k = with_slice ? fill_complete_kernel<true, true> : fill_complete_kernel<false, true>;
     else
-        k = with_slice ? fill_complete_kernel<true, false> : fill_complete_kernel<false, false>;
+        k = with_slice ? fill_complete_kernel<true> : fill_complete_kernel<false>;
     PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
     PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));

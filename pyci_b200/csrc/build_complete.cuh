@@ -200,32 +200,15 @@ string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W,
 struct CompleteSmem {
     size_t tables, slice, rowbuf, total;
     u32 MP;
-    // prefetch buffers of the beta-side data of a row (two per group; PF kernels): offsets inside one buffer
-    size_t pf, pf_dv, pf_sub, pf_pos, pf_terms;
 };
-// Lb > 0: with the prefetch buffers (beta list length Lb, sub-list length L1b, nb beta electrons)
-__host__ __device__ inline CompleteSmem complete_smem(u32 nSa, u32 nDa, u32 n, u32 M, int groups, bool with_slice,
-                                                      u32 Lb = 0, u32 L1b = 0, u32 nb = 0) {
+__host__ __device__ inline CompleteSmem complete_smem(u32 nSa, u32 nDa, u32 n, u32 M, int groups, bool with_slice) {
     CompleteSmem L;
     L.tables = (16 * (size_t)nSa + 8 * (size_t)nDa + 8 * (size_t)(nSa + nDa + n * n) + 15) & ~(size_t)15;
     L.slice = with_slice ? 8 * (size_t)nSa * n * n : 0;
     L.MP = (M + 8) & ~3u; // room for the alignment shift (<= 3 entries), multiple of 4 entries
     L.rowbuf = 12 * (size_t)L.MP;
-    auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    L.pf_dv = a16(4 * (size_t)Lb);               // [0, pf_dv): colex ranks of the beta list
-    L.pf_sub = L.pf_dv + a16(8 * (size_t)Lb);    // values of its doubles
-    L.pf_pos = L.pf_sub + a16(8 * (size_t)L1b);  // sub-list entries
-    L.pf_terms = L.pf_pos + a16(4 * (size_t)L1b); // positions of the sub-list in the full list
-    L.pf = Lb ? L.pf_terms + a16(8 * (size_t)L1b * (nb ? nb : 1)) : 0; // own-spin terms of the beta singles
-    L.total = L.tables + L.slice + (size_t)groups * (L.rowbuf + 2 * L.pf);
+    L.total = L.tables + L.slice + (size_t)groups * L.rowbuf;
     return L;
-}
-
-__device__ __forceinline__ void cp_async4(void *dst_shared, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst_shared, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
 }
 
 __device__ __forceinline__ double flip_sign(double x, u32 signbit31) { // signbit31: 0 or 1 << 31
@@ -256,17 +239,12 @@ __device__ __forceinline__ void bar_full_arrive(int group) {
 // (Measured and dropped, profiles/r2e: letting all 256 threads of the group copy the finished row out with 16-byte
 // st.global -- the faster of the two in the bare store probe tools/write_bw.cu, 6.19 against 5.85 TB/s -- costs a
 // second full barrier per row and the copy on every warp's critical path: 7.29 ms against 5.09 ms with the bulk copies.)
-// PF: the beta-side data of a row (its colex-rank list, double-excitation values, sub-list, positions, own-spin terms:
-// ~5 KB at n = 14) is copied into shared memory by cp.async WHILE THE PREVIOUS ROW OF THE GROUP IS BEING BUILT, two
-// buffers per group, so that no row waits for an L2 round trip: the per-row dependency chain of a group, not the
-// instruction count, is what sets this kernel's pace.
-template<bool SLICE, bool PF>
+template<bool SLICE>
 __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = C.nn;
-    const CompleteSmem SL = PF ? complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE, Lb, L1b, nb)
-                               : complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
+    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
     uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
     double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
@@ -277,7 +255,6 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     const u32 t = threadIdx.x & 255u, wq = 7u - (t >> 5), lane = t & 31u;
     double *sval = reinterpret_cast<double *>(smem_raw + SL.tables + SL.slice + (size_t)group * SL.rowbuf);
     int *scol = reinterpret_cast<int *>(sval + SL.MP);
-    unsigned char *pfbase = smem_raw + SL.tables + SL.slice + (size_t)G * SL.rowbuf + (size_t)group * 2 * SL.pf;
 
     const long n1 = P.n, n2 = n1 * n1, n3 = n2 * n1;
     const double *__restrict__ two_mo = P.two_mo;
@@ -334,67 +311,35 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
         __syncthreads();
         const long blo = max(rbeg, (long)ra * Nb - P.row0), bhi = min(rend, (long)(ra + 1) * Nb - P.row0);
         u32 rb = (u32)(P.row0 + blo + group - (long)ra * Nb);
-        // PF: copies of the beta-side data of row-in-block rbx into prefetch buffer `which` (every thread its share)
-        auto prefetch = [&](u32 rbx, int which) {
-            unsigned char *pb = pfbase + (size_t)which * SL.pf;
-            const u32 *gcr = C.B.cr + rbx * Lb;
-            const double *gdv = C.B.dval + rbx * Lb;
-            for (u32 w = t; w < Lb; w += 256) {
-                cp_async4(reinterpret_cast<u32 *>(pb) + w, gcr + w);
-                cp_async8(reinterpret_cast<double *>(pb + SL.pf_dv) + w, gdv + w);
-            }
-            const uint2 *gsub = C.B.sub + rbx * L1b;
-            const u32 *gpos = C.B.pos1 + rbx * L1b;
-            for (u32 w = t; w < L1b; w += 256) {
-                cp_async8(reinterpret_cast<uint2 *>(pb + SL.pf_sub) + w, gsub + w);
-                cp_async4(reinterpret_cast<u32 *>(pb + SL.pf_pos) + w, gpos + w);
-            }
-            const double *gt = C.B.terms + (size_t)rbx * L1b * nb;
-            for (u32 w = t; w < L1b * nb; w += 256)
-                cp_async8(reinterpret_cast<double *>(pb + SL.pf_terms) + w, gt + w);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        int par = 0;
-        if (PF && blo + group < bhi)
-            prefetch(rb, 0); // first row of this group in the block: nothing to overlap it with
-        for (long r = blo + group; r < bhi; r += G, rb += (u32)G, par ^= 1) {
+        for (long r = blo + group; r < bhi; r += G, rb += (u32)G) {
             // ---- this row's beta-side data: every global load is issued before anything waits
-            const unsigned char *pb = pfbase + (size_t)par * SL.pf;
-            const u32 *__restrict__ crB = PF ? reinterpret_cast<const u32 *>(pb) : C.B.cr + rb * Lb;
-            const double *__restrict__ dvalB = PF ? reinterpret_cast<const double *>(pb + SL.pf_dv) : C.B.dval + rb * Lb;
-            const uint2 *__restrict__ subB = PF ? reinterpret_cast<const uint2 *>(pb + SL.pf_sub) : C.B.sub + rb * L1b;
-            const u32 *__restrict__ pos1B = PF ? reinterpret_cast<const u32 *>(pb + SL.pf_pos) : C.B.pos1 + rb * L1b;
-            const double *__restrict__ termsB = PF ? reinterpret_cast<const double *>(pb + SL.pf_terms)
-                                                   : C.B.terms + (size_t)rb * L1b * nb;
+            const u32 *__restrict__ crB = C.B.cr + rb * Lb;
+            const double *__restrict__ dvalB = C.B.dval + rb * Lb;
+            const uint2 *__restrict__ subB = C.B.sub + rb * L1b;
             const u64 Bdet = __ldg(P.dets + 2 * (P.row0 + r) + 1);
             const u32 j1s = __ldg(C.B.j1self + rb);
             uint2 eb = make_uint2(0u, 0u);
+            if (ab_active && w0 < L1b)
+                eb = __ldg(subB + w0);
             u32 cb[2] = {0u, 0u};
             double dv[2] = {0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) // the first 512 entries of the beta list (the rest, if any, below)
+                if (tA + 256u * q < Lb) {
+                    cb[q] = __ldg(crB + tA + 256u * q);
+                    dv[q] = __ldg(dvalB + tA + 256u * q);
+                }
             u32 ps = 0u, sgn1 = 0u;
             double tq[4] = {0.0, 0.0, 0.0, 0.0}, diag_r = 0.0;
-            if (tB < L1b)
+            if (tB < L1b) { // beta single tB of the sub-list (:382-394): position, parity, its first own-spin terms
+                ps = __ldg(C.B.pos1 + rb * L1b + tB);
+                sgn1 = __ldg(subB + tB).y & 0x80000000u;
+                const double *tb = C.B.terms + (size_t)(rb * L1b + tB) * nb;
+#pragma unroll
+                for (u32 q = 0; q < 4; ++q)
+                    if (q < nb)
+                        tq[q] = __ldg(tb + q);
                 diag_r = __ldg(P.diag + r);
-            if (!PF) {
-                if (ab_active && w0 < L1b)
-                    eb = __ldg(subB + w0);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) // the first 512 entries of the beta list (the rest, if any, below)
-                    if (tA + 256u * q < Lb) {
-                        cb[q] = __ldg(crB + tA + 256u * q);
-                        dv[q] = __ldg(dvalB + tA + 256u * q);
-                    }
-                if (tB < L1b) { // beta single tB of the sub-list (:382-394): position, parity, its first own-spin terms
-                    ps = __ldg(pos1B + tB);
-                    sgn1 = __ldg(subB + tB).y & 0x80000000u;
-                    const double *tb = termsB + (size_t)tB * nb;
-#pragma unroll
-                    for (u32 q = 0; q < 4; ++q)
-                        if (q < nb)
-                            tq[q] = __ldg(tb + q);
-                }
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory"); // this thread's share of the current row's data
             }
             const long out0 = r * (long)M; // complete space: every row holds M entries
             const u32 ov = (u32)out0 & 1u, oc = (u32)out0 & 3u;
@@ -408,29 +353,6 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                 __syncwarp();
             }
             bar_free_sync(group);
-            if (PF) {
-                // every thread's copies of this row are visible now, and all warps have left the previous row: its
-                // prefetch buffer takes the next row of the group while this one is built
-                if (r + G < bhi)
-                    prefetch(rb + (u32)G, par ^ 1);
-                if (ab_active && w0 < L1b)
-                    eb = subB[w0];
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    if (tA + 256u * q < Lb) {
-                        cb[q] = crB[tA + 256u * q];
-                        dv[q] = dvalB[tA + 256u * q];
-                    }
-                if (tB < L1b) {
-                    ps = pos1B[tB];
-                    sgn1 = subB[tB].y & 0x80000000u;
-                    const double *tb = termsB + (size_t)tB * nb;
-#pragma unroll
-                    for (u32 q = 0; q < 4; ++q)
-                        if (q < nb)
-                            tq[q] = tb[q];
-                }
-            }
             // (the prefetched beta-side values are consumed first so that their registers are free in the walk below)
             // ---- A' = A: columns of the whole beta list, values of its doubles (:397-416)
 #pragma unroll
@@ -443,22 +365,22 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                 }
             }
             for (u32 w = tA + 512u; w < Lb; w += 256) {
-                const u32 c2 = crB[w];
+                const u32 c2 = __ldg(crB + w);
                 bcol[self_off + w] = (int)(self_colbase + (c2 & 0x7fffffffu));
                 if (c2 >> 31)
-                    bval[self_off + w] = dvalB[w];
+                    bval[self_off + w] = __ldg(dvalB + w);
             }
             // ---- values of the beta singles (:382-394) and of the diagonal (:421-424)
             for (u32 j1 = tB; j1 < L1b; j1 += 256) {
                 if (j1 != tB) {
-                    ps = pos1B[j1];
-                    sgn1 = subB[j1].y & 0x80000000u;
+                    ps = __ldg(C.B.pos1 + rb * L1b + j1);
+                    sgn1 = __ldg(subB + j1).y & 0x80000000u;
                 }
                 const u32 slot = self_off + (ps & 0xffffu);
                 if (j1 == j1s) {
                     bval[slot] = (j1 == tB) ? diag_r : P.diag[r];
                 } else {
-                    const double *tb = termsB + (size_t)j1 * nb;
+                    const double *tb = C.B.terms + (size_t)(rb * L1b + j1) * nb;
                     double v = JA[ps >> 16];
                     if (j1 == tB) {
 #pragma unroll
@@ -466,10 +388,10 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                             if (q < nb)
                                 v += tq[q];
                         for (u32 q = 4; q < nb; ++q)
-                            v += tb[q];
+                            v += __ldg(tb + q);
                     } else {
                         for (u32 q = 0; q < nb; ++q)
-                            v += tb[q];
+                            v += __ldg(tb + q);
                     }
                     bval[slot] = flip_sign(v, sgn1);
                 }
@@ -480,7 +402,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             if (ab_active) {
                 for (u32 w = w0; w < L1b; w += 256) {
                     if (w != w0)
-                        eb = subB[w]; // colex rank | parity << 31, n i + a << 18, n^2 i + a
+                        eb = __ldg(subB + w); // colex rank | parity << 31, n i + a << 18, n^2 i + a
                     if (w == j1s)
                         continue; // B' = B: the alpha single below
                     const u32 kl = SLICE ? ((eb.y >> 18) & 0xfffu) : (eb.y & 0x3ffffu);
