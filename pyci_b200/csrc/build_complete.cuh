@@ -238,7 +238,10 @@ __device__ __forceinline__ void bar_full_arrive(int group) {
 // 8-byte stores to rows that start at arbitrary offsets reach only a third of the HBM write bandwidth).
 // (Measured and dropped, profiles/r2e: letting all 256 threads of the group copy the finished row out with 16-byte
 // st.global -- the faster of the two in the bare store probe tools/write_bw.cu, 6.19 against 5.85 TB/s -- costs a
-// second full barrier per row and the copy on every warp's critical path: 7.29 ms against 5.09 ms with the bulk copies.)
+// second full barrier per row and the copy on every warp's critical path: 7.29 ms against 5.09 ms with the bulk copies.
+// Likewise measured and dropped, profiles/r2h: cp.async prefetch of the NEXT row's beta-side data (~5 KB) into two
+// shared-memory buffers per group while the current row is built, so that no row waits for an L2 round trip: 5.89 ms
+// against 5.04 ms -- the exposed load latency is not what sets the pace; the extra ~800 copy instructions per row are.)
 template<bool SLICE>
 __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
