@@ -61,6 +61,17 @@ int upload(T **dst, const T *src, size_t count, cudaStream_t st) {
     return PYCI_OK;
 }
 
+// flag |= 1 when two_mo[i,k,a,l] != two_mo[i,l,a,k] somewhere (bit patterns compared)
+__global__ void kl_symmetry_kernel(const double *__restrict__ two_mo, long n, int *flag) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long n2 = n * n, n3 = n2 * n;
+    if (idx >= n2 * n2)
+        return;
+    const long i = idx / n3, k = (idx / n2) % n, a = (idx / n) % n, l = idx % n;
+    if (k < l && __double_as_longlong(two_mo[idx]) != __double_as_longlong(two_mo[i * n3 + l * n2 + a * n + k]))
+        atomicOr(flag, 1);
+}
+
 __global__ void export_lower_kernel(const long *__restrict__ indptr, const int *__restrict__ cols,
                                     const double *__restrict__ vals, const int *__restrict__ take,
                                     const long *__restrict__ outptr, long *__restrict__ out_idx,
@@ -256,10 +267,20 @@ int pyci_ham_upload(pyci_ctx *ctx, long nbasis, double ecore, const double *one_
         rc = upload(&ham->v, v, n2, ctx->stream);
     if (w && rc == PYCI_OK)
         rc = upload(&ham->w, w, n2, ctx->stream);
+    int *dflag = nullptr, hflag = 1;
+    if (rc == PYCI_OK && two_mo && dev_malloc(&dflag, sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream);
+        const long total = (long)(n2 * n2);
+        kl_symmetry_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ham->two_mo, nbasis, dflag);
+        ctx->launches++;
+        cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    }
     if (rc == PYCI_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         pyci_set_error("CUDA error while uploading integrals: %s", cudaGetErrorString(cudaGetLastError()));
         rc = PYCI_ERR_CUDA;
     }
+    ham->kl_sym = two_mo && dflag && hflag == 0;
+    dev_free(dflag);
     if (rc != PYCI_OK) {
         pyci_ham_destroy(ham);
         return rc;

@@ -673,9 +673,12 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     const size_t table_bytes = ((size_t)Na * S.La + (size_t)Nb * S.Lb) * 32 + (size_t)Na * L1a * (32 + 8 * P.nocc_a) +
                                (size_t)Nb * L1b * (32 + 8 * P.nocc_b);
     // groups of 256 threads per CTA (one CTA per SM) and whether the two_mo slice of an alpha string fits beside them
+    // slices of k <= l only when the integrals allow it (pyci_ham::kl_sym) -- PYCI_B200_NO_PACKED_SLICE keeps n^2
+    const bool packed = P.kl_sym && !getenv("PYCI_B200_NO_PACKED_SLICE") && P.n * (P.n + 1) / 2 < 4096;
+    const u32 nsl = packed ? (u32)(P.n * (P.n + 1) / 2) : (u32)(P.n * P.n);
     auto fit = [&](bool sl) {
         for (int g = 4; g >= 1; --g)
-            if ((long)complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, g, sl).total <= (long)ctx->smem_optin)
+            if ((long)complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, g, sl, nsl).total <= (long)ctx->smem_optin)
                 return g;
         return 0;
     };
@@ -690,7 +693,7 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     if (!groups || S.La > 65535u || S.Lb > 65535u || P.n * P.n >= 4096 || S.M >= (1u << 30) ||
         table_bytes > ((size_t)4 << 30) || (long)tsmem > (long)ctx->smem_optin)
         return PYCI_OK; // the general sorted path takes it
-    const size_t fsmem = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice).total;
+    const size_t fsmem = complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, groups, with_slice, nsl).total;
     CompleteParams C;
     memset(&C, 0, sizeof(C));
     int rc = alloc_string_tables(C.A, Na, S.La, L1a, (u32)P.nocc_a, P.nSa, P.nDa);
@@ -705,16 +708,18 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.Nb = Nb;
     C.dSb = P.dSb;
     C.nn = (u32)(P.n * P.n);
+    C.nsl = nsl;
+    C.packed = packed ? 1u : 0u;
     C.GP = std::max(1u, 256u / L1b);
-    C.GPnn = C.GP * C.nn;
+    C.GPnn = C.GP * nsl;
     C.GPw = std::max(1u, 192u / L1b);
-    C.GPwnn = C.GPw * C.nn;
+    C.GPwnn = C.GPw * nsl;
     C.dL1b = make_fastdiv(L1b);
     PYCI_CUDA(cudaFuncSetAttribute(string_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
     string_table_kernel<<<std::min<u32>(Na, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.A, 0, (long)Nb, S.Wa, S.K1, S.binom,
-                                                                               S.Lb, L1b);
+                                                                               S.Lb, L1b, (int)packed);
     string_table_kernel<<<std::min<u32>(Nb, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.B, 1, 1L, S.Wb, S.K1, S.binom,
-                                                                               S.La, L1a);
+                                                                               S.La, L1a, (int)packed);
     ctx->launches += 2;
     const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
     PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
@@ -1273,6 +1278,7 @@ int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_
     P.ncol = op->ncol;
     P.one_mo = ham->one_mo;
     P.two_mo = ham->two_mo;
+    P.kl_sym = ham->kl_sym ? 1 : 0;
     P.h = ham->h;
     P.v = ham->v;
     P.w = ham->w;

@@ -49,8 +49,12 @@ struct CompleteParams {
     u32 Nb; // C(n, nocc_b)
     FastDiv dSb;
     // launch-time constants of the fill kernel (kept out of registers: the compiler re-derives them per use)
-    u32 nn, GP, GPnn; // n^2; walkers side by side in the alpha-beta segment = max(1, 256 / L1b); GP * n^2
+    u32 nn, GP, GPnn; // n^2; walkers side by side in the alpha-beta segment = max(1, 256 / L1b); GP * nsl
     u32 GPw, GPwnn;   // the same for the warp-specialised kernel (192 alpha-beta threads per group)
+    // slice of one alpha single i -> a in shared memory: two_mo[i, k, a, l] over (k, l).  When the integrals satisfy
+    // <ik|al> = <il|ak> bit for bit (checked at upload; real orbitals do) only k <= l is kept, n (n + 1) / 2 doubles
+    // at l (l + 1) / 2 + k instead of n^2: 51 KB instead of 98 KB at n = 16, which is a fourth row buffer per SM
+    u32 nsl, packed;
     FastDiv dL1b;     // division of the thread index by L1b
 };
 
@@ -62,7 +66,7 @@ inline size_t string_table_smem(u32 W, u32 L, u32 n, u32 K1, size_t pair_bytes) 
 // rank.  other_L / other_L1: sizes of the A' = A and A' = single groups when this string is the alpha side.
 __global__ void __launch_bounds__(128)
 string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W, u32 K1, const u32 *gbinom, u32 other_L,
-                    u32 other_L1) {
+                    u32 other_L1, int packed) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32 *bm = reinterpret_cast<u32 *>(smem_raw);
     u32 *pf = bm + W;
@@ -156,7 +160,11 @@ string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W,
                 }
                 T.cr[base + j] = cr;
                 T.dval[base + j] = 0.0;
-                T.sub[base1 + j1] = make_uint2(cr, (par << 31) | ((u32)(n1 * i + a) << 18) | (u32)(n2 * i + a));
+                // (bits 18-29: offset of (i, a) inside a slice two_mo[i', :, a', :] -- n i + a, or the packed index
+                // of the unordered pair when the slices keep k <= l only)
+                const u32 hi = (u32)max(i, a), lo = (u32)min(i, a);
+                const u32 in_slice = packed ? hi * (hi + 1) / 2 + lo : (u32)(n1 * i + a);
+                T.sub[base1 + j1] = make_uint2(cr, (par << 31) | (in_slice << 18) | (u32)(n2 * i + a));
                 T.pos1[base1 + j1] = j | ((u32)(n1 * i + a) << 16);
                 const size_t g = (size_t)s * nS + (j1 - (j1 > j1s ? 1u : 0u));
                 T.s_aux[g] = (par << 31) | (u32)(n3 * i + n1 * a);
@@ -201,10 +209,11 @@ struct CompleteSmem {
     size_t tables, slice, rowbuf, total;
     u32 MP;
 };
-__host__ __device__ inline CompleteSmem complete_smem(u32 nSa, u32 nDa, u32 n, u32 M, int groups, bool with_slice) {
+__host__ __device__ inline CompleteSmem complete_smem(u32 nSa, u32 nDa, u32 n, u32 M, int groups, bool with_slice,
+                                                      u32 nsl) {
     CompleteSmem L;
     L.tables = (16 * (size_t)nSa + 8 * (size_t)nDa + 8 * (size_t)(nSa + nDa + n * n) + 15) & ~(size_t)15;
-    L.slice = with_slice ? 8 * (size_t)nSa * n * n : 0;
+    L.slice = with_slice ? 8 * (size_t)nSa * nsl : 0;
     L.MP = (M + 8) & ~3u; // room for the alignment shift (<= 3 entries), multiple of 4 entries
     L.rowbuf = 12 * (size_t)L.MP;
     L.total = L.tables + L.slice + (size_t)groups * L.rowbuf;
@@ -247,7 +256,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = C.nn;
-    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
+    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE, C.nsl);
+    const u32 nsl = C.nsl;
     uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
     double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
@@ -304,8 +314,20 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             }
             if (SLICE) {
                 double *wslice = const_cast<double *>(slice);
-                for (u32 q = threadIdx.x; q < nSa * nn; q += blockDim.x) {
-                    const u32 g = q / nn, kl = q - g * nn, k = kl / (u32)n1, l = kl - k * (u32)n1;
+                for (u32 q = threadIdx.x; q < nSa * nsl; q += blockDim.x) {
+                    const u32 g = q / nsl, kl = q - g * nsl;
+                    u32 k, l;
+                    if (C.packed) { // kl = l (l + 1) / 2 + k, k <= l
+                        l = (u32)((sqrtf(8.0f * (float)kl + 1.0f) - 1.0f) * 0.5f);
+                        while ((l + 1) * (l + 2) / 2 <= kl)
+                            ++l;
+                        while (l * (l + 1) / 2 > kl)
+                            --l;
+                        k = kl - l * (l + 1) / 2;
+                    } else {
+                        k = kl / (u32)n1;
+                        l = kl - k * (u32)n1;
+                    }
                     wslice[q] = two_mo[(C.A.s_aux[bS + g] & 0x7fffffffu) + n2 * k + l];
                 }
             }
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     int *pc = bcol + w;
                     double *pv = bval + w;
                     const uint4 *pa = s_pack + gq;
-                    const double *psl = slice + gq * nn + kl;
+                    const double *psl = slice + gq * nsl + kl;
 #pragma unroll 4
                     for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += C.GPnn) {
                         const uint4 a = *pa;
@@ -444,7 +466,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     double v = s_pre[g];
                     for (u64 q = Bdet; q; q &= q - 1) {
                         const u32 kk = (u32)__ffsll((long long)q) - 1u;
-                        v += SLICE ? slice[g * nn + kk * (u32)n1 + kk] : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
+                        v += SLICE ? slice[g * nsl + (C.packed ? kk * (kk + 1) / 2 + kk : kk * (u32)n1 + kk)]
+                                   : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
                     }
                     const u32 slot = a.x + j1s;
                     bcol[slot] = (int)(a.y + rb);
@@ -505,7 +528,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_ws_kernel(BuildParams P
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = C.nn;
-    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE);
+    const CompleteSmem SL = complete_smem(nSa, nDa, (u32)P.n, M, G, SLICE, C.nsl);
+    const u32 nsl = C.nsl;
     uint4 *s_pack = reinterpret_cast<uint4 *>(smem_raw); // [nSa] first slot, colex(A') * Nb, n^3 i + n a, parity << 31
     uint2 *d_pack = reinterpret_cast<uint2 *>(s_pack + nSa); // [nDa] slot | colex(A') * Nb
     double *s_pre = reinterpret_cast<double *>(d_pack + nDa);
@@ -555,8 +579,20 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_ws_kernel(BuildParams P
             }
             if (SLICE) {
                 double *wslice = const_cast<double *>(slice);
-                for (u32 q = threadIdx.x; q < nSa * nn; q += blockDim.x) {
-                    const u32 g = q / nn, kl = q - g * nn, k = kl / (u32)n1, l = kl - k * (u32)n1;
+                for (u32 q = threadIdx.x; q < nSa * nsl; q += blockDim.x) {
+                    const u32 g = q / nsl, kl = q - g * nsl;
+                    u32 k, l;
+                    if (C.packed) { // kl = l (l + 1) / 2 + k, k <= l
+                        l = (u32)((sqrtf(8.0f * (float)kl + 1.0f) - 1.0f) * 0.5f);
+                        while ((l + 1) * (l + 2) / 2 <= kl)
+                            ++l;
+                        while (l * (l + 1) / 2 > kl)
+                            --l;
+                        k = kl - l * (l + 1) / 2;
+                    } else {
+                        k = kl / (u32)n1;
+                        l = kl - k * (u32)n1;
+                    }
                     wslice[q] = two_mo[(C.A.s_aux[bS + g] & 0x7fffffffu) + n2 * k + l];
                 }
             }
@@ -617,7 +653,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_ws_kernel(BuildParams P
                         int *pc = bcol + w;
                         double *pv = bval + w;
                         const uint4 *pa = s_pack + gq;
-                        const double *psl = slice + gq * nn + kl;
+                        const double *psl = slice + gq * nsl + kl;
 #pragma unroll 4
                         for (u32 g = gq; g < nSa; g += GP, pa += GP, psl += C.GPwnn) {
                             const uint4 a = *pa;
@@ -706,7 +742,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_ws_kernel(BuildParams P
                     double v = s_pre[g];
                     for (u64 q = Bdet; q; q &= q - 1) {
                         const u32 kk = (u32)__ffsll((long long)q) - 1u;
-                        v += SLICE ? slice[g * nn + kk * (u32)n1 + kk] : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
+                        v += SLICE ? slice[g * nsl + (C.packed ? kk * (kk + 1) / 2 + kk : kk * (u32)n1 + kk)]
+                                   : __ldg(two_mo + a.z + (u32)n2 * kk + kk);
                     }
                     const u32 slot = a.x + j1s;
                     bcol[slot] = (int)(a.y + rb);

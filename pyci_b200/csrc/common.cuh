@@ -76,6 +76,8 @@ struct pyci_ham {
     long nbasis = 0;
     double ecore = 0.0;
     double *one_mo = nullptr, *two_mo = nullptr, *h = nullptr, *v = nullptr, *w = nullptr;
+    bool kl_sym = false; // two_mo[i,k,a,l] == two_mo[i,l,a,k] bit for bit, all indices (checked at upload): the
+                         // complete-space fill may then keep only k <= l of its shared-memory integral slices
 };
 
 // how determinant strings are packed into hash keys

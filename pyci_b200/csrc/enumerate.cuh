@@ -32,6 +32,7 @@ struct BuildParams {
     u32 nSa, nSb, nDa, nDb, nAB, nPva, nPvb, ncand;
     long row0, nloc, ncol;
     const double *one_mo, *two_mo, *h, *v, *w;
+    int kl_sym; // two_mo[i,k,a,l] == two_mo[i,l,a,k] for all indices (pyci_ham::kl_sym)
     long *indptr;
     int *cols;
     double *vals;

@@ -357,3 +357,38 @@ def test_rows_too_long_for_shared_memory_go_through_hbm(monkeypatch, kind, n, oc
         op = pyci.sparse_op(ham, wfn)
         assert np.array_equal(op.indptr(), oi) and np.array_equal(op.indices(), ox) and np.array_equal(op.data(), od), join
         monkeypatch.delenv(join)
+
+
+@pytest.mark.parametrize("sym", ["none", "kl-only", "8-fold", "8-fold+noslice"])
+def test_complete_fill_with_and_without_integral_symmetry(monkeypatch, sym):
+    """The reference indexes two_mo with no symmetry assumption (sparseop.cpp:287,307,332,352).  The complete-space fill
+    keeps only k <= l of its shared-memory slices two_mo[i, :, a, :] when <ik|al> == <il|ak> holds bit for bit (checked
+    at upload, pyci_ham::kl_sym) and the full n^2 otherwise: arbitrary integrals, integrals with just that symmetry and
+    8-fold symmetric ones give the oracle's operator bit for bit."""
+    import pyci_b200 as pyci
+    n, occ = 9, (3, 3)
+    rng = np.random.default_rng(77)
+    if sym.startswith("8-fold"):
+        ecore, one, two = O.synthetic_integrals(n, 5)
+    else:
+        ecore = 0.5
+        one = rng.standard_normal((n, n))
+        two = rng.standard_normal((n, n, n, n))
+        if sym == "kl-only":
+            two = np.ascontiguousarray(two + two.transpose(0, 3, 2, 1))  # two[i,k,a,l] == two[i,l,a,k] exactly
+            assert np.array_equal(two, two.transpose(0, 3, 2, 1))
+    if sym.endswith("noslice"):
+        monkeypatch.setenv("PYCI_B200_NO_SLICE", "1")
+    ham = pyci.hamiltonian(ecore, one, two)
+    wfn = pyci.fullci_wfn(n, *occ)
+    wfn.add_all_dets()
+    for kw in (dict(), dict(symmetric=False)):
+        op = pyci.sparse_op(ham, wfn, **kw)
+        assert op.stats()["fill_kernel"] == "fill_complete_kernel"
+        oi, ox, od = O.sparse_op(O.FULLCI, n, occ[0], occ[1], wfn.to_det_array(), (one, two), **kw)
+        assert np.array_equal(op.indptr(), oi) and np.array_equal(op.indices(), ox)
+        assert np.array_equal(op.data(), od), sym
+    monkeypatch.setenv("PYCI_B200_NO_PACKED_SLICE", "1")
+    op = pyci.sparse_op(ham, wfn)
+    oi, ox, od = O.sparse_op(O.FULLCI, n, occ[0], occ[1], wfn.to_det_array(), (one, two))
+    assert np.array_equal(op.data(), od)
