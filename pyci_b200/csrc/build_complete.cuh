@@ -213,7 +213,7 @@ __host__ __device__ inline CompleteSmem complete_smem(u32 nSa, u32 nDa, u32 n, u
                                                       u32 nsl) {
     CompleteSmem L;
     L.tables = (16 * (size_t)nSa + 8 * (size_t)nDa + 8 * (size_t)(nSa + nDa + n * n) + 15) & ~(size_t)15;
-    L.slice = with_slice ? 8 * (size_t)nSa * nsl : 0;
+    L.slice = with_slice ? (8 * (size_t)nSa * nsl + 15) & ~(size_t)15 : 0; // the row buffers behind it stay 16-byte aligned
     L.MP = (M + 8) & ~3u; // room for the alignment shift (<= 3 entries), multiple of 4 entries
     L.rowbuf = 12 * (size_t)L.MP;
     L.total = L.tables + L.slice + (size_t)groups * L.rowbuf;
