@@ -676,12 +676,22 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     // slices of k <= l only when the integrals allow it (pyci_ham::kl_sym) -- PYCI_B200_NO_PACKED_SLICE keeps n^2
     const bool packed = P.kl_sym && !getenv("PYCI_B200_NO_PACKED_SLICE") && P.n * (P.n + 1) / 2 < 4096;
     const u32 nsl = packed ? (u32)(P.n * (P.n + 1) / 2) : (u32)(P.n * P.n);
-    auto fit = [&](bool sl) {
-        for (int g = 4; g >= 1; --g)
+    // threads per group: 256 (at most four groups per CTA), or 128 when shared memory has room for at least six row
+    // buffers -- more rows in flight per SM (PYCI_B200_FILL_GT=128/256 overrides; the warp-specialised form has 256)
+    int gt = 256;
+    auto fit_gt = [&](bool sl, int gth) {
+        for (int g = std::min(1024 / gth, 7); g >= 1; --g) // (two named barriers per group, sixteen per CTA)
             if ((long)complete_smem(P.nSa, P.nDa, (u32)P.n, S.M, g, sl, nsl).total <= (long)ctx->smem_optin)
                 return g;
         return 0;
     };
+    if (!getenv("PYCI_B200_FILL_WS")) {
+        if (const char *e = getenv("PYCI_B200_FILL_GT"))
+            gt = atoi(e) == 128 ? 128 : 256;
+        else if (fit_gt(true, 128) >= 6 && L1b <= 128u)
+            gt = 128;
+    }
+    auto fit = [&](bool sl) { return fit_gt(sl, gt); };
     bool with_slice = !getenv("PYCI_B200_NO_SLICE");
     int groups = with_slice ? fit(true) : 0;
     if (groups < 2) { // the slice leaves room for fewer than two row buffers: integrals through L1/L2 instead
@@ -710,7 +720,7 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.nn = (u32)(P.n * P.n);
     C.nsl = nsl;
     C.packed = packed ? 1u : 0u;
-    C.GP = std::max(1u, 256u / L1b);
+    C.GP = std::max(1u, (u32)gt / L1b);
     C.GPnn = C.GP * nsl;
     C.GPw = std::max(1u, 192u / L1b);
     C.GPwnn = C.GPw * nsl;
@@ -730,10 +740,12 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     void (*k)(BuildParams, CompleteParams, int);
     if (!v1)
         k = with_slice ? fill_complete_ws_kernel<true> : fill_complete_ws_kernel<false>;
+    else if (gt == 128)
+        k = with_slice ? fill_complete_kernel<true, 128> : fill_complete_kernel<false, 128>;
     else
-        k = with_slice ? fill_complete_kernel<true> : fill_complete_kernel<false>;
+        k = with_slice ? fill_complete_kernel<true, 256> : fill_complete_kernel<false, 256>;
     PYCI_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    k<<<(unsigned)grid, 256 * groups, fsmem, st>>>(P, C, groups);
+    k<<<(unsigned)grid, gt * groups, fsmem, st>>>(P, C, groups);
     PYCI_CUDA(cudaEventRecord(ctx->ev[5], st));
     ctx->launches++;
     PYCI_CUDA(cudaGetLastError());

@@ -227,14 +227,17 @@ __device__ __forceinline__ double flip_sign(double x, u32 signbit31) { // signbi
 // Two named barriers per group of 256 threads.  FREE: the row buffer may be overwritten (all eight warps wait;
 // warp 0 gets there after the bulk stores of the previous row have read the buffer).  FULL: the row is
 // complete -- warps 1-7 only arrive and move on to the next row's loads, warp 0 waits and launches the TMA.
+template<int GT = 256>
 __device__ __forceinline__ void bar_free_sync(int group) {
-    asm volatile("bar.sync %0, 256;" ::"r"(2 * group + 1) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(2 * group + 1), "n"(GT) : "memory");
 }
+template<int GT = 256>
 __device__ __forceinline__ void bar_full_sync(int group) {
-    asm volatile("bar.sync %0, 256;" ::"r"(2 * group + 2) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(2 * group + 2), "n"(GT) : "memory");
 }
+template<int GT = 256>
 __device__ __forceinline__ void bar_full_arrive(int group) {
-    asm volatile("bar.arrive %0, 256;" ::"r"(2 * group + 2) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(2 * group + 2), "n"(GT) : "memory");
 }
 
 // One CTA per SM; rows [row0, row0 + nloc) are split into one contiguous range per CTA, so a CTA changes alpha
@@ -251,8 +254,13 @@ __device__ __forceinline__ void bar_full_arrive(int group) {
 // Likewise measured and dropped, profiles/r2h: cp.async prefetch of the NEXT row's beta-side data (~5 KB) into two
 // shared-memory buffers per group while the current row is built, so that no row waits for an L2 round trip: 5.89 ms
 // against 5.04 ms -- the exposed load latency is not what sets the pace; the extra ~800 copy instructions per row are.)
-template<bool SLICE>
-__global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
+// GT: threads per group (256 or 128).  The pace of a group is set by the dependency chain of its row, not by its
+// instruction count, so when shared memory has room for more row buffers than 1024 / 256 groups can use, smaller groups
+// -- more rows in flight per SM -- are tried (run_complete picks; PYCI_B200_FILL_GT overrides).
+template<bool SLICE, int GT>
+__global__ void __launch_bounds__(GT == 128 ? 896 : 1024, 1) fill_complete_kernel(BuildParams P, CompleteParams C, int G) {
+    constexpr u32 NW = GT / 32; // warps per group (a power of two)
+    constexpr int NQ = 512 / GT; // entries of the beta list a thread loads before the row barrier
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 nSa = C.A.nS, nDa = C.A.nD, Lb = C.B.L, L1b = C.B.L1, nb = C.B.nocc, M = C.M, Nb = C.Nb;
     const u32 nn = C.nn;
@@ -264,8 +272,8 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     double *d_val = s_pre + nSa;
     double *JA = d_val + nDa; // [n][n] one_mo[i,a] + sum_{k in A} <ik|ak>
     const double *slice = reinterpret_cast<const double *>(smem_raw + SL.tables); // [nSa][n][n]
-    const int group = threadIdx.x >> 8;
-    const u32 t = threadIdx.x & 255u, wq = 7u - (t >> 5), lane = t & 31u;
+    const int group = threadIdx.x / GT;
+    const u32 t = threadIdx.x % GT, wq = (NW - 1u) - (t >> 5), lane = t & 31u;
     double *sval = reinterpret_cast<double *>(smem_raw + SL.tables + SL.slice + (size_t)group * SL.rowbuf);
     int *scol = reinterpret_cast<int *>(sval + SL.MP);
 
@@ -278,15 +286,15 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
     // alpha-beta doubles: a thread keeps ONE entry of the beta sub-list (L1b <= 256) and walks the alpha singles
     // g = gq, gq + GP, ...; 256 / L1b such walkers side by side
     const u32 GP = C.GP;
-    const u32 gq = (L1b <= 256u) ? fdiv(t, C.dL1b) : 0u;
-    const u32 w0 = (L1b <= 256u) ? t - gq * L1b : t;
-    const bool ab_active = (L1b > 256u) || gq < GP;
+    const u32 gq = (L1b <= (u32)GT) ? fdiv(t, C.dL1b) : 0u;
+    const u32 w0 = (L1b <= (u32)GT) ? t - gq * L1b : t;
+    const bool ab_active = (L1b > (u32)GT) || gq < GP;
     const u32 Uda = (nDa + 31) >> 5, Usa = (nSa + 31) >> 5;
     // Work balance inside a group (all eight warps meet at the FULL barrier of every row, so the slowest warp sets
     // the pace): the alpha-beta walk loads every warp alike; the short segments are dealt to different warps through
     // rotated thread indices -- the second trip of the A' = A list to warps 3-4 (tA), the beta singles to warps 1-2
     // (tB), the alpha-side units from warp 7 downwards (wq) -- and warp 0 keeps the bulk stores.
-    const u32 tA = (t + 160u) & 255u, tB = (t + 224u) & 255u;
+    const u32 tA = (t + 5u * GT / 8u) % GT, tB = (t + 7u * GT / 8u) % GT;
     const u32 ra_first = (u32)((P.row0 + rbeg) / Nb), ra_last = (u32)((P.row0 + rend - 1) / Nb);
     for (u32 ra = ra_first; ra <= ra_last; ++ra) {
         // ---- stage the alpha string's tables
@@ -346,14 +354,17 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             uint2 eb = make_uint2(0u, 0u);
             if (ab_active && w0 < L1b)
                 eb = __ldg(subB + w0);
-            u32 cb[2] = {0u, 0u};
-            double dv[2] = {0.0, 0.0};
+            u32 cb[NQ];
+            double dv[NQ];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) // the first 512 entries of the beta list (the rest, if any, below)
-                if (tA + 256u * q < Lb) {
-                    cb[q] = __ldg(crB + tA + 256u * q);
-                    dv[q] = __ldg(dvalB + tA + 256u * q);
+            for (int q = 0; q < NQ; ++q) { // the first 512 entries of the beta list (the rest, if any, below)
+                cb[q] = 0u;
+                dv[q] = 0.0;
+                if (tA + (u32)GT * q < Lb) {
+                    cb[q] = __ldg(crB + tA + (u32)GT * q);
+                    dv[q] = __ldg(dvalB + tA + (u32)GT * q);
                 }
+            }
             u32 ps = 0u, sgn1 = 0u;
             double tq[4] = {0.0, 0.0, 0.0, 0.0}, diag_r = 0.0;
             if (tB < L1b) { // beta single tB of the sub-list (:382-394): position, parity, its first own-spin terms
@@ -377,26 +388,26 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
             }
-            bar_free_sync(group);
+            bar_free_sync<GT>(group);
             // (the prefetched beta-side values are consumed first so that their registers are free in the walk below)
             // ---- A' = A: columns of the whole beta list, values of its doubles (:397-416)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const u32 w = tA + 256u * q;
+            for (int q = 0; q < NQ; ++q) {
+                const u32 w = tA + (u32)GT * q;
                 if (w < Lb) {
                     bcol[self_off + w] = (int)(self_colbase + (cb[q] & 0x7fffffffu));
                     if (cb[q] >> 31)
                         bval[self_off + w] = dv[q];
                 }
             }
-            for (u32 w = tA + 512u; w < Lb; w += 256) {
+            for (u32 w = tA + 512u; w < Lb; w += GT) {
                 const u32 c2 = __ldg(crB + w);
                 bcol[self_off + w] = (int)(self_colbase + (c2 & 0x7fffffffu));
                 if (c2 >> 31)
                     bval[self_off + w] = __ldg(dvalB + w);
             }
             // ---- values of the beta singles (:382-394) and of the diagonal (:421-424)
-            for (u32 j1 = tB; j1 < L1b; j1 += 256) {
+            for (u32 j1 = tB; j1 < L1b; j1 += GT) {
                 if (j1 != tB) {
                     ps = __ldg(C.B.pos1 + rb * L1b + j1);
                     sgn1 = __ldg(subB + j1).y & 0x80000000u;
@@ -425,7 +436,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             // one add (column), one xor (sign) and two shared stores through pointers that already hold the beta
             // entry's position w -- everything that depends on w alone is hoisted out of the walk over g
             if (ab_active) {
-                for (u32 w = w0; w < L1b; w += 256) {
+                for (u32 w = w0; w < L1b; w += GT) {
                     if (w != w0)
                         eb = __ldg(subB + w); // colex rank | parity << 31, n i + a << 18, n^2 i + a
                     if (w == j1s)
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             // down (it holds the idle lanes of the walk above): warp-uniform control flow.
             u32 ubase = 0;
             // ---- alpha-alpha doubles (:339-358)
-            for (u32 u = (wq - ubase) & 7u; u < Uda; u += 8) {
+            for (u32 u = (wq - ubase) & (NW - 1u); u < Uda; u += NW) {
                 const u32 d = u * 32 + lane;
                 if (d < nDa) {
                     const uint2 dp = d_pack[d];
@@ -459,7 +470,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             }
             ubase += Uda;
             // ---- alpha singles (:303-315)
-            for (u32 u = (wq - ubase) & 7u; u < Usa; u += 8) {
+            for (u32 u = (wq - ubase) & (NW - 1u); u < Usa; u += NW) {
                 const u32 g = u * 32 + lane;
                 if (g < nSa) {
                     const uint4 a = s_pack[g];
@@ -478,9 +489,9 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             // column streams; the few entries before / after the aligned bodies by scalar stores
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (t >= 32) {
-                bar_full_arrive(group);
+                bar_full_arrive<GT>(group);
             } else {
-                bar_full_sync(group);
+                bar_full_sync<GT>(group);
                 const u32 hv = ov, nv = (M - hv) >> 1;                    // values: pairs
                 const u32 hc = min(M, (4u - oc) & 3u), nc = (M - hc) >> 2; // columns: quads
                 if (t == 0) {
@@ -508,7 +519,7 @@ __global__ void __launch_bounds__(1024, 1) fill_complete_kernel(BuildParams P, C
             }
         }
     }
-    if ((threadIdx.x & 255u) == 0)
+    if (threadIdx.x % GT == 0)
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all rows written before the CTA retires
 }
 
