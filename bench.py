@@ -449,8 +449,11 @@ def gate_rows(row0, nloc, nb, rng, target):
             bounds = np.concatenate([bounds, rng.choice(cb, min(24, len(cb)), replace=False)])
     for b in bounds:
         rows.update((int(b) - 1, int(b), int(b) + 1))
-    rows.update(int(r) for r in rng.integers(row0, row0 + nloc, max(0, target - len(rows))))
-    return np.array(sorted(r for r in rows if row0 <= r < row0 + nloc), dtype=np.int64)
+    rows = {r for r in rows if row0 <= r < row0 + nloc}
+    want = min(target, nloc)
+    while len(rows) < want:  # random rest (collisions are redrawn)
+        rows.update(int(r) for r in rng.integers(row0, row0 + nloc, want - len(rows)))
+    return np.array(sorted(rows), dtype=np.int64)
 
 
 def parity_gate(B, spec, op, dwfn, kind, host, target):

@@ -46,3 +46,35 @@ def test_reference_arm_on_other_ranks_is_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload",
                           "cfg1", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_parity_gate_row_sample_covers_the_boundaries():
+    """bench.gate_rows: first / last rows of the shard, both sides of alpha-string boundaries and of uniform CTA-range
+    boundaries, random rest; every row inside the shard, sorted, unique."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    row0, nloc, nb = 414050, 414050, 1820  # rank 1 of 8 at config 4
+    rows = bench.gate_rows(row0, nloc, nb, rng, 1000)
+    assert len(rows) >= 1000 and np.all(np.diff(rows) > 0) and rows[0] == row0 and rows[-1] == row0 + nloc - 1
+    bounds = np.arange(-(-row0 // nb) * nb, row0 + nloc, nb)
+    hit = [b for b in bounds if b in rows and b - 1 in rows]
+    assert len(hit) >= 20  # alpha-string boundaries, both sides
+    per = -(-nloc // 148)
+    assert any((row0 + per * k) in rows for k in range(1, 148))
+    assert len(bench.gate_rows(5, 0, 7, rng, 100)) == 0
+    small = bench.gate_rows(0, 3, 0, rng, 50)
+    assert small.tolist() == [0, 1, 2]
+
+
+def test_golden_e0_lookup():
+    for key, n in (("cfg3", 14), ("syn10", 10)):
+        spec = bench.workload_spec(key)
+        spec["key"] = key
+        e0, tol, src = bench.golden_e0(spec)
+        assert e0 is not None and tol == 1e-10 and "e0_syn.json" in src
+    spec = bench.workload_spec("cfg1")
+    spec["key"] = "cfg1"
+    assert bench.golden_e0(spec)[0] == -14.617409507  # pyci/test/test_routines.py:44
+    spec = bench.workload_spec("cfg4")
+    spec["key"] = "cfg4"
+    assert bench.golden_e0(spec) == (None, None, None)
