@@ -16,6 +16,7 @@
 // The table grows by re-running the pass when it fills (the load is not known before the walk).  Row-sharded
 // over ranks: every rank walks its own rows, the compacted external lists are all-gathered and merged.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -578,13 +579,29 @@ int exchange_to_owners(pyci_ctx *ctx, bool two, ExtList &L, ExtList &owned) {
                 owner_scatter_kernel<false><<<blocks, 256, 0, st>>>(L.pay, L.k0, L.k1, L.n, (u32)R, dcnt + R, spay, s0, s1);
             ctx->launches++;
         }
+        const bool trace = getenv("PYCI_B200_HCI_TRACE") != nullptr;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double tt = now();
+        if (trace) {
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[pyci_b200 hci] rank %d:   partition by owner done (send %ld, receive %ld)\n", me, soff[(size_t)R], roff[(size_t)R]);
+            tt = now();
+        }
         PYCI_TRY(comm_alltoallv_u64(ctx, spay, scount.data(), soff.data(), rpay, rcount.data(), roff.data()));
         PYCI_TRY(comm_alltoallv_u64(ctx, s0, scount.data(), soff.data(), r0, rcount.data(), roff.data()));
         if (two)
             PYCI_TRY(comm_alltoallv_u64(ctx, s1, scount.data(), soff.data(), r1, rcount.data(), roff.data()));
         PYCI_CUDA(cudaStreamSynchronize(st)); // hcur is read by the copy above
+        if (trace) {
+            fprintf(stderr, "[pyci_b200 hci] rank %d:   all-to-all %.2f ms\n", me, 1e3 * (now() - tt));
+            tt = now();
+        }
         const std::vector<long> one(1, roff[(size_t)R]);
         PYCI_TRY(merge_lists<MODE>(ctx, two, rpay, r0, r1, nr, one, owned));
+        if (trace) {
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[pyci_b200 hci] rank %d:   merge at the owner %.2f ms (%ld owned)\n", me, 1e3 * (now() - tt), owned.n);
+        }
         return PYCI_OK;
     };
     const int rc = body();
@@ -729,7 +746,16 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
         }
         return PYCI_OK;
     };
+    // PYCI_B200_HCI_TRACE: host wall time per phase on stderr (each phase closed by a stream synchronisation)
+    const bool trace = getenv("PYCI_B200_HCI_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     int rc = body();
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[pyci_b200 hci] rank %d: walk + local merge %.2f ms (%ld entries)\n", ctx->rank, 1e3 * (now() - t0), L.n);
+        t0 = now();
+    }
     if (R > 1) {
         // a rank-local failure of the walk (table growth out of memory, ...) must not leave the other ranks waiting
         // in the exchange: agree on the status first, every rank fails together
@@ -744,6 +770,11 @@ int collect_external(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, co
     }
     if (rc == PYCI_OK)
         rc = exchange();
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[pyci_b200 hci] rank %d: exchange to owners%s %.2f ms (%ld entries)\n", ctx->rank,
+                MODE == MODE_HCI ? " + all-gather" : "", 1e3 * (now() - t0), L.n);
+    }
     for (ExtList &q : parts)
         q.release();
     dev_free(gp);
