@@ -664,7 +664,7 @@ void free_string_tables(StringTables &T) {
     memset(&T, 0, sizeof(T));
 }
 
-int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, size_t pair_bytes, int *used) {
+int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, size_t pair_bytes, int *used, bool *diag_done) {
     PYCI_NVTX("pyci:fill(complete: string tables + fill_complete_kernel)");
     cudaStream_t st = ctx->stream;
     *used = 0;
@@ -725,12 +725,20 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.GPw = std::max(1u, 192u / L1b);
     C.GPwnn = C.GPw * nsl;
     C.dL1b = make_fastdiv(L1b);
-    PYCI_CUDA(cudaFuncSetAttribute(string_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-    string_table_kernel<<<std::min<u32>(Na, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.A, 0, (long)Nb, S.Wa, S.K1, S.binom,
-                                                                               S.Lb, L1b, (int)packed);
-    string_table_kernel<<<std::min<u32>(Nb, 4u * ctx->sm_count), 128, tsmem, st>>>(P, C.B, 1, 1L, S.Wb, S.K1, S.binom,
-                                                                               S.La, L1a, (int)packed);
-    ctx->launches += 2;
+    {
+        PrepParams Q;
+        Q.ga = std::min<u32>(Na, 4u * ctx->sm_count);
+        Q.gb = std::min<u32>(Nb, 4u * ctx->sm_count);
+        Q.Wa = S.Wa, Q.Wb = S.Wb, Q.K1 = S.K1, Q.La = S.La, Q.Lb = S.Lb, Q.L1a = L1a, Q.L1b = L1b;
+        Q.stride_a = (long)Nb;
+        Q.binom = S.binom;
+        Q.packed = (int)packed;
+        const long gd = *diag_done ? 0 : (P.nloc + 127) / 128;
+        PYCI_CUDA(cudaFuncSetAttribute(complete_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        complete_prep_kernel<<<(unsigned)(Q.ga + Q.gb + gd), 128, tsmem, st>>>(P, C.A, C.B, Q);
+        *diag_done = true;
+        ctx->launches++;
+    }
     const long grid = std::min<long>((P.nloc + groups - 1) / groups, (long)ctx->sm_count);
     PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
     // PYCI_B200_FILL_WS: the warp-specialised form of the kernel instead of the default one (every warp passes through
@@ -900,8 +908,15 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     std::vector<u32> hb; // binomial table staged for the string-table pre-pass (lives until the final synchronise)
     bool fill_timed = false;
     if (nloc > 0 && nnz > 0) {
-        diag_kernel<KIND><<<(unsigned)((nloc + 127) / 128), 128, 0, st>>>(P);
-        ctx->launches++;
+        // H_ii of the rows: its own launch, except on the complete path, whose table launch computes it as well
+        bool diag_done = false;
+        auto ensure_diag = [&]() {
+            if (!diag_done) {
+                diag_kernel<KIND><<<(unsigned)((nloc + 127) / 128), 128, 0, st>>>(P);
+                ctx->launches++;
+                diag_done = true;
+            }
+        };
         bool done = false;
         if constexpr (KIND == PYCI_FULLCI) {
             // sorted two-spin wave function: slots in sorted order from two per-row rank lists (build_sorted.cuh)
@@ -931,7 +946,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 if (direct && !getenv("PYCI_B200_NO_COMPLETE_PATH")) {
                     // complete space: per-string tables + slot-ordered fill (build_complete.cuh)
                     int used = 0;
-                    PYCI_TRY(run_complete(ctx, P, S, pair_bytes, &used));
+                    PYCI_TRY(run_complete(ctx, P, S, pair_bytes, &used, &diag_done));
                     done = used != 0;
                     if (done) {
                         op->fill_kernel = "fill_complete_kernel";
@@ -939,6 +954,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     }
                 }
                 if (!done && (long)smem <= (long)ctx->smem_optin) {
+                    ensure_diag();
                     if (!direct) {
                         PYCI_TRY(wfn_ensure_index(wfn));
                         ix = make_index<KM>(wfn);
@@ -967,6 +983,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             }
         }
         if (!done) {
+            ensure_diag();
             PYCI_TRY(wfn_ensure_index(wfn));
             ix = make_index<KM>(wfn);
             int block = pick_block(std::max<long>((long)P.ncand / 4, maxrow));

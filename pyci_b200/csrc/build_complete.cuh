@@ -62,11 +62,12 @@ inline size_t string_table_smem(u32 W, u32 L, u32 n, u32 K1, size_t pair_bytes) 
     return 4 * (size_t)(4 * W + 3 * L + n * K1) + pair_bytes + 16;
 }
 
-// One CTA per string.  spin = 0 reads the alpha string of row rank * stride, spin = 1 the beta string of row
-// rank.  other_L / other_L1: sizes of the A' = A and A' = single groups when this string is the alpha side.
-__global__ void __launch_bounds__(128)
-string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W, u32 K1, const u32 *gbinom, u32 other_L,
-                    u32 other_L1, int packed) {
+// One CTA per string (CTA `bid` of `nb`, 128 threads).  spin = 0 reads the alpha string of row rank * stride,
+// spin = 1 the beta string of row rank.  other_L / other_L1: sizes of the A' = A and A' = single groups when this
+// string is the alpha side.
+__device__ __forceinline__ void string_table_body(const BuildParams &P, const StringTables &T, int spin, long stride, u32 W,
+                                                  u32 K1, const u32 *gbinom, u32 other_L, u32 other_L1, int packed, u32 bid,
+                                                  u32 nb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32 *bm = reinterpret_cast<u32 *>(smem_raw);
     u32 *pf = bm + W;
@@ -89,7 +90,7 @@ string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W,
     fill_pairs(pairs, P.npairs_dim);
     for (u32 t = threadIdx.x; t < (u32)P.n * K1; t += blockDim.x)
         binom[t] = gbinom[t];
-    for (u32 s = blockIdx.x; s < T.N; s += gridDim.x) {
+    for (u32 s = bid; s < T.N; s += nb) {
         __syncthreads();
         const u64 S = (spin == 0) ? P.dets[2 * ((long)s * stride)] : P.dets[2 * (long)s + 1];
         if (threadIdx.x == 0) {
@@ -200,6 +201,29 @@ string_table_kernel(BuildParams P, StringTables T, int spin, long stride, u32 W,
                 T.s_off[(size_t)s * nS + (j1 - (j1 > j1s ? 1u : 0u))] = off;
             else
                 T.d_off[(size_t)s * nD + (j - j1)] = off;
+        }
+    }
+}
+
+// Everything the fill kernel reads that is not the determinant list, in one launch of independent CTAs: the string
+// tables of both spins (CTAs [0, ga) and [ga, ga + gb)) and the diagonal H_ii of this rank's rows (the rest, 128 rows
+// per CTA) -- three launches that each under-fill the GPU for ~20-50 us became one.
+struct PrepParams {
+    u32 ga, gb, Wa, Wb, K1, La, Lb, L1a, L1b;
+    long stride_a;
+    const u32 *binom;
+    int packed;
+};
+__global__ void __launch_bounds__(128) complete_prep_kernel(BuildParams P, StringTables A, StringTables B, PrepParams Q) {
+    if (blockIdx.x < Q.ga) {
+        string_table_body(P, A, 0, Q.stride_a, Q.Wa, Q.K1, Q.binom, Q.Lb, Q.L1b, Q.packed, blockIdx.x, Q.ga);
+    } else if (blockIdx.x < Q.ga + Q.gb) {
+        string_table_body(P, B, 1, 1L, Q.Wb, Q.K1, Q.binom, Q.La, Q.L1a, Q.packed, blockIdx.x - Q.ga, Q.gb);
+    } else {
+        const long r = (long)(blockIdx.x - Q.ga - Q.gb) * 128 + threadIdx.x;
+        if (r < P.nloc) {
+            const long row = P.row0 + r;
+            P.diag[r] = diag_twobody(P, P.dets[2 * row], P.dets[2 * row + 1]);
         }
     }
 }
