@@ -186,6 +186,8 @@ void pyci_ctx_destroy(pyci_ctx *ctx) {
     for (int i = 0; i < 6; ++i)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
+    if (ctx->binom_dev)
+        cudaFree(ctx->binom_dev);
     if (ctx->own_stream && ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;

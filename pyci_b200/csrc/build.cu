@@ -720,6 +720,10 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.nn = (u32)(P.n * P.n);
     C.nsl = nsl;
     C.packed = packed ? 1u : 0u;
+    {
+        const char *e = getenv("PYCI_B200_FILL_L2HINT");
+        C.l2hint = (e && atoi(e) == 0) ? 0u : 1u;
+    }
     C.GP = std::max(1u, (u32)gt / L1b);
     C.GPnn = C.GP * nsl;
     C.GPw = std::max(1u, 192u / L1b);
@@ -727,8 +731,8 @@ int run_complete(pyci_ctx *ctx, const BuildParams &P, const SortedParams &S, siz
     C.dL1b = make_fastdiv(L1b);
     {
         PrepParams Q;
-        Q.ga = std::min<u32>(Na, 4u * ctx->sm_count);
-        Q.gb = std::min<u32>(Nb, 4u * ctx->sm_count);
+        Q.ga = std::min<u32>(Na, 16u * ctx->sm_count); // (a string is ~10 us of dependent phases: one CTA each)
+        Q.gb = std::min<u32>(Nb, 16u * ctx->sm_count);
         Q.Wa = S.Wa, Q.Wb = S.Wb, Q.K1 = S.K1, Q.La = S.La, Q.Lb = S.Lb, Q.L1a = L1a, Q.L1b = L1b;
         Q.stride_a = (long)Nb;
         Q.binom = S.binom;
@@ -905,7 +909,7 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
     }
     PYCI_CUDA(cudaEventRecord(ctx->ev[2], st)); // after the allocations: ev[2]..ev[3] brackets kernels only
     u64 *long_scratch = nullptr; // row buffers in HBM for rows too long for shared memory (freed after the fill)
-    std::vector<u32> hb; // binomial table staged for the string-table pre-pass (lives until the final synchronise)
+    std::vector<u32> hb; // binomial table staged for the string-table pre-pass
     bool fill_timed = false;
     if (nloc > 0 && nnz > 0) {
         // H_ii of the rows: its own launch, except on the complete path, whose table launch computes it as well
@@ -931,14 +935,22 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 S.K1 = (u32)std::max(P.nocc_a, P.nocc_b) + 1;
                 S.M = P.ncand + 1;
                 S.Nb = (u32)Ub;
-                hb.resize((size_t)P.n * S.K1);
-                for (int pp = 0; pp < P.n; ++pp)
-                    for (u32 j = 0; j < S.K1; ++j)
-                        hb[(size_t)pp * S.K1 + j] = (u32)std::min(binom_d(pp, j), 4294967295.0);
-                u32 *dbinom = nullptr;
-                PYCI_CUDA(dev_malloc(&dbinom, sizeof(u32) * hb.size()));
-                PYCI_CUDA(cudaMemcpyAsync(dbinom, hb.data(), sizeof(u32) * hb.size(), cudaMemcpyHostToDevice, st));
-                S.binom = dbinom;
+                if (!ctx->binom_dev || ctx->binom_n != P.n || ctx->binom_k1 != (int)S.K1) {
+                    hb.resize((size_t)P.n * S.K1);
+                    for (int pp = 0; pp < P.n; ++pp)
+                        for (u32 j = 0; j < S.K1; ++j)
+                            hb[(size_t)pp * S.K1 + j] = (u32)std::min(binom_d(pp, j), 4294967295.0);
+                    PYCI_CUDA(cudaStreamSynchronize(st)); // a build in flight may still read the table being replaced
+                    if (ctx->binom_dev)
+                        cudaFree(ctx->binom_dev);
+                    ctx->binom_dev = nullptr;
+                    PYCI_CUDA(cudaMalloc(&ctx->binom_dev, sizeof(u32) * hb.size()));
+                    PYCI_CUDA(cudaMemcpyAsync(ctx->binom_dev, hb.data(), sizeof(u32) * hb.size(), cudaMemcpyHostToDevice, st));
+                    PYCI_CUDA(cudaStreamSynchronize(st));
+                    ctx->binom_n = P.n;
+                    ctx->binom_k1 = (int)S.K1;
+                }
+                S.binom = ctx->binom_dev;
                 const int block = pick_block((long)P.ncand / 4);
                 // PYCI_B200_FORCE_PROBE: resolve columns through the hash index even in a complete space
                 const bool direct = analytic && !getenv("PYCI_B200_FORCE_PROBE");
@@ -979,7 +991,6 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     done = true;
                     op->fill_kernel = "fill_sorted_kernel";
                 }
-                dev_free(dbinom); // stream-ordered; hb outlives the copy (synchronised at the end of the build)
             }
         }
         if (!done) {

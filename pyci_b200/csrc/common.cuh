@@ -69,6 +69,12 @@ struct pyci_ctx {
     int sm_count = 148;
     int smem_optin = 0; // max dynamic shared memory per block (opt-in)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // binomial table C(p, j), p < binom_n, j < binom_k1, of the last sorted-space build (the same for every build of
+    // one problem size: uploaded once instead of once per construction)
+    unsigned *binom_dev = nullptr;
+    int binom_n = 0, binom_k1 = 0;
+    // slots of the external-space table that held the last walk of ext_hint_rows rows (hci.cu: first guess of the next)
+    long ext_hint_rows = -1, ext_hint_cap = 0;
 };
 
 struct pyci_ham {

@@ -480,7 +480,15 @@ int walk_rows(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P, const OrderPar
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const long budget = std::max<long>(1L << 16, (long)(free_b / 8 / 24));
-    long cap = std::max<long>(1L << 16, next_pow2(std::min<long>(64 * std::max<long>(nloc, 1), budget) / 2 + 1));
+    // (a rank that walks 1/R of the rows still finds most of the external space -- the duplicates it no longer sees are
+    // the ones the other ranks' rows would have produced -- so a row-sharded walk sizes its table for R times its rows:
+    // a table that is too large costs a memset and a scan, one that is too small costs a whole second walk.  At 8 GPUs
+    // the 100 376-determinant case of bench.py walked three times, 60 ms instead of 20.)
+    const long rows_guess = std::min<long>(std::max<long>(wfn->ndet, 1), std::max<long>(nloc, 1) * std::max(ctx->nranks, 1));
+    long cap = std::max<long>(1L << 16, next_pow2(std::min<long>(64 * rows_guess, budget)));
+    // the size that held the last walk of this many rows (compute_enpt2 followed by add_hci, repeated selection steps)
+    if (ctx->ext_hint_rows == nloc && ctx->ext_hint_cap > cap)
+        cap = ctx->ext_hint_cap;
     ExtBuffers E;
     for (;;) {
         if (cap > (1L << 31))
@@ -498,6 +506,8 @@ int walk_rows(pyci_ctx *ctx, const pyci_wfn *wfn, BuildParams &P, const OrderPar
         E.release();
         cap *= 4;
     }
+    ctx->ext_hint_rows = nloc;
+    ctx->ext_hint_cap = cap;
     const int rc = compact(ctx, E, out);
     E.release();
     if (rc != PYCI_OK)

@@ -100,6 +100,76 @@ __global__ void k_staged(int *cols, double *vals, long nrow, int M) {
     }
     if (STAGE == 1 && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+// variants of the TMA-staged row store: bulk stores cut into CHUNK-byte pieces (0 = one per array), an L2 evict-first
+// hint, and a main body that starts and ends on 128-byte lines of global memory (ALIGN = 128; 16 = as the product does)
+template<int CHUNK, int HINT, int ALIGN>
+__global__ void k_staged_v(int *cols, double *vals, long nrow, int M) {
+    extern __shared__ __align__(16) unsigned char sm[]; // (the base of dynamic shared memory is 1 KB aligned here: no static shared memory)
+    const int MP = (M + 32 + 31) & ~31;
+    double *sval[2] = {reinterpret_cast<double *>(sm), reinterpret_cast<double *>(sm) + MP};
+    int *scol[2] = {reinterpret_cast<int *>(sm + 16 * MP), reinterpret_cast<int *>(sm + 16 * MP) + MP};
+    const long per = (nrow + gridDim.x - 1) / gridDim.x;
+    const long r0 = blockIdx.x * per, r1 = min(nrow, r0 + per);
+    unsigned long long pol = 0;
+    if (HINT) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    int buf = 0;
+    const int AV = ALIGN / 8, AC = ALIGN / 4; // elements per alignment unit
+    for (long r = r0; r < r1; ++r, buf ^= 1) {
+        const long out0 = r * M;
+        // shared-memory images keep the global address modulo ALIGN
+        const int ov = (int)(out0 % AV), oc = (int)(out0 % AC);
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        for (int e = threadIdx.x; e < M; e += blockDim.x) {
+            sval[buf][ov + e] = (double)e;
+            scol[buf][oc + e] = e;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int hv = (AV - ov) % AV, nv = (M - hv) / AV * AV;
+        const int hc = (AC - oc) % AC, nc = (M - hc) / AC * AC;
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const int cv = CHUNK ? CHUNK : nv * 8, cc = CHUNK ? CHUNK : nc * 4;
+            const int nchv = (nv * 8 + cv - 1) / cv, nchc = (nc * 4 + cc - 1) / cc;
+            for (int q = lane; q < nchv + nchc; q += 32) {
+                const bool isv = q < nchv;
+                const int k = isv ? q : q - nchv;
+                const int off = k * (isv ? cv : cc);
+                const int len = min(isv ? cv : cc, (isv ? nv * 8 : nc * 4) - off);
+                const char *g = isv ? (const char *)(vals + out0 + hv) + off : (const char *)(cols + out0 + hc) + off;
+                const unsigned sa = isv ? smem_u32(sval[buf] + ov + hv) + off : smem_u32(scol[buf] + oc + hc) + off;
+                if (HINT)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(g),
+                                 "r"(sa), "r"(len), "l"(pol) : "memory");
+                else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(sa), "r"(len) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // heads and tails by scalar stores (up to ALIGN bytes each)
+            for (int e = lane; e < hv; e += 32) vals[out0 + e] = sval[buf][ov + e];
+            for (int e = hv + nv + lane; e < M; e += 32) vals[out0 + e] = sval[buf][ov + e];
+            for (int e = lane; e < hc; e += 32) cols[out0 + e] = scol[buf][oc + e];
+            for (int e = hc + nc + lane; e < M; e += 32) cols[out0 + e] = scol[buf][oc + e];
+        }
+    }
+    if (threadIdx.x < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+template<int CHUNK, int HINT, int ALIGN>
+void run_v(const char *label, int *cols, double *vals, long nrow, int M, cudaEvent_t a, cudaEvent_t b) {
+    const int MP = (M + 32 + 31) & ~31;
+    const size_t smem = 24 * (size_t)MP;
+    cudaFuncSetAttribute(k_staged_v<CHUNK, HINT, ALIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int g = 3; g <= 4; ++g) {
+        float ms;
+        cudaEventRecord(a);
+        k_staged_v<CHUNK, HINT, ALIGN><<<148 * g, 256, smem>>>(cols, vals, nrow, M);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        printf("%-40s x%d %8.3f ms %8.1f GB/s  %s\n", label, g, ms, (double)nrow * M * 12 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
+}
 #define TIME(label, bytes, ...)                                                              \
     do {                                                                                     \
         cudaEventRecord(a); __VA_ARGS__; cudaEventRecord(b); cudaEventSynchronize(b);         \
@@ -136,6 +206,14 @@ int main() {
             TIME(l, nnz * 12, (k_staged<2><<<148 * g, 256, smem>>>(cols, vals, nrow, M)));
         }
     }
+    for (int rep = 0; rep < 2; ++rep) {
+        run_v<0, 0, 16>("TMA whole arrays, 16 B aligned", cols, vals, nrow, M, a, b);
+        run_v<0, 1, 16>("TMA whole, evict-first hint", cols, vals, nrow, M, a, b);
+        run_v<2048, 0, 16>("TMA 2 KB pieces", cols, vals, nrow, M, a, b);
+        run_v<4096, 0, 16>("TMA 4 KB pieces", cols, vals, nrow, M, a, b);
+        run_v<4096, 1, 16>("TMA 4 KB pieces, evict-first hint", cols, vals, nrow, M, a, b);
+        // (main bodies on 128-byte lines of global memory: 5390 / 5820 GB/s at x3 / x4, below the 16-byte form)
+    }
     // check the staged TMA variant wrote what the scalar variant writes
     k_rows<0><<<148 * 4, 256>>>(cols, vals, nrow, M);
     double *ref = new double[4 * M]; int *refc = new int[4 * M];
@@ -148,5 +226,14 @@ int main() {
     long bad = 0;
     for (int i = 0; i < 4 * M; ++i) bad += (ref[i] != got[i]) + (refc[i] != gotc[i]);
     printf("TMA staged mismatches: %ld  %s\n", bad, cudaGetErrorString(cudaDeviceSynchronize()));
+    {
+        const int MP2 = (M + 32 + 31) & ~31;
+        cudaMemset(vals + off, 0, 4 * M * 8); cudaMemset(cols + off, 0, 4 * M * 4);
+        k_staged_v<4096, 1, 16><<<148 * 3, 256, 24 * (size_t)MP2>>>(cols, vals, nrow, M);
+        cudaMemcpy(got, vals + off, 4 * M * 8, cudaMemcpyDeviceToHost); cudaMemcpy(gotc, cols + off, 4 * M * 4, cudaMemcpyDeviceToHost);
+        bad = 0;
+        for (int i = 0; i < 4 * M; ++i) bad += (ref[i] != got[i]) + (refc[i] != gotc[i]);
+        printf("TMA pieces + hint mismatches: %ld  %s\n", bad, cudaGetErrorString(cudaDeviceSynchronize()));
+    }
     return 0;
 }
