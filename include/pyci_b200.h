@@ -15,6 +15,7 @@
 #ifndef PYCI_B200_H
 #define PYCI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -66,6 +67,12 @@ PYCI_API int pyci_ctx_synchronize(pyci_ctx *ctx);
  * Memory the pool holds is invisible to other allocators of the process (torch's caching allocator, cudaMalloc):
  * this hands everything that is not in use back to the driver. */
 PYCI_API int pyci_ctx_release_memory(pyci_ctx *ctx);
+/* Page-locked host memory for the buffers a binding hands to the export calls (pyci_op_export_csr, ...): every entry
+ * point accepts any host pointer, but a device-to-host copy into pageable memory goes through the driver's bounce
+ * buffers at about a quarter of the PCIe rate.  The host module keeps a small pool of these for the row pointer it
+ * returns (the reference returns a numpy array over its own vector: pyci/src/binding.cpp:520-528). */
+PYCI_API int pyci_host_alloc(void **ptr, size_t bytes);
+PYCI_API void pyci_host_free(void *ptr);
 /* Row-sharding across `nranks` processes (one per GPU of one box).  unique_id: the 128 bytes of an
  * ncclUniqueId made by pyci_nccl_unique_id() on rank 0 and handed to the other ranks by the caller
  * (torch.distributed broadcast, MPI, a file ...).  Collective: every rank must call it. */

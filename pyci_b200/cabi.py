@@ -36,6 +36,8 @@ PROTOTYPES = {
     "pyci_ctx_destroy": (None, [_vp]),
     "pyci_ctx_synchronize": (_i, [_vp]),
     "pyci_ctx_release_memory": (_i, [_vp]),
+    "pyci_host_alloc": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]),
+    "pyci_host_free": (None, [_vp]),
     "pyci_nccl_unique_id": (_i, [_vp]),
     "pyci_ctx_init_comm": (_i, [_vp, _i, _i, _vp]),
     "pyci_ctx_rank": (_i, [_vp]),

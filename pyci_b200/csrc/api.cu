@@ -199,6 +199,19 @@ int pyci_ctx_synchronize(pyci_ctx *ctx) {
     return PYCI_OK;
 }
 
+int pyci_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr)
+        PYCI_FAIL(PYCI_ERR_VALUE, "null argument");
+    *ptr = nullptr;
+    PYCI_CUDA(cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+    return PYCI_OK;
+}
+
+void pyci_host_free(void *ptr) {
+    if (ptr)
+        cudaFreeHost(ptr);
+}
+
 int pyci_ctx_release_memory(pyci_ctx *ctx) {
     if (!ctx)
         PYCI_FAIL(PYCI_ERR_VALUE, "null argument");

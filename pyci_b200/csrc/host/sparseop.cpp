@@ -4,6 +4,8 @@
 // (rdm.cpp:1011-1055).  All numerical work happens in libpyci_b200.so on the GPU.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "pyci_host.h"
@@ -13,6 +15,73 @@ namespace pyci_host {
 namespace {
 
 pyci_ctx *g_ctx = nullptr;
+
+// Page-locked buffers behind the numpy arrays the export methods return (the row pointer: 8 MB at a million rows).
+// A copy from the device into a fresh pageable array pays the page faults of the array and the driver's bounce
+// buffers; into page-locked memory it runs at the PCIe rate.  A page-locked allocation costs about a millisecond, so
+// the buffers are recycled: the capsule that owns an array's memory hands it back here when numpy drops the array.
+// (Never destroyed: buffers still cached at interpreter exit are left to the process teardown.)
+struct PinnedPool {
+    static constexpr size_t MAX_CACHED = (size_t)256 << 20, MAX_ONE = (size_t)64 << 20;
+    std::mutex m;
+    std::vector<std::pair<size_t, void *>> cache;
+    size_t cached = 0;
+    void *get(size_t bytes, size_t *cap) {
+        size_t c = 4096;
+        while (c < bytes)
+            c <<= 1;
+        *cap = c;
+        {
+            std::lock_guard<std::mutex> lock(m);
+            for (size_t i = 0; i < cache.size(); ++i)
+                if (cache[i].first == c) {
+                    void *p = cache[i].second;
+                    cache[i] = cache.back();
+                    cache.pop_back();
+                    cached -= c;
+                    return p;
+                }
+        }
+        void *p = nullptr;
+        return pyci_host_alloc(&p, c) == PYCI_OK ? p : nullptr;
+    }
+    void put(void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (cached + cap <= MAX_CACHED) {
+                cache.emplace_back(cap, p);
+                cached += cap;
+                return;
+            }
+        }
+        pyci_host_free(p);
+    }
+};
+PinnedPool &pinned_pool() {
+    static PinnedPool *pool = new PinnedPool;
+    return *pool;
+}
+struct PinnedBlock {
+    void *p;
+    size_t cap;
+};
+
+// a 1-d int64 array of n elements over page-locked memory (plain numpy memory when it is large or unavailable)
+Array<long> pinned_long_array(long n) {
+    const size_t bytes = sizeof(long) * (size_t)std::max<long>(n, 1);
+    if (bytes <= PinnedPool::MAX_ONE && !std::getenv("PYCI_B200_NO_PINNED_RESULTS")) {
+        size_t cap = 0;
+        if (void *p = pinned_pool().get(bytes, &cap)) {
+            py::capsule owner(new PinnedBlock{p, cap}, [](void *q) {
+                PinnedBlock *b = static_cast<PinnedBlock *>(q);
+                pinned_pool().put(b->p, b->cap);
+                delete b;
+            });
+            return py::array_t<long>({(py::ssize_t)n}, {(py::ssize_t)sizeof(long)}, static_cast<long *>(p), owner);
+        }
+    }
+    return Array<long>(n);
+}
 
 struct DeviceHam {
     pyci_ham *h = nullptr;
@@ -186,7 +255,7 @@ py::tuple SparseOp::py_solve_ci(long n, py::object c0, long ncv, long maxiter, d
 }
 
 Array<long> SparseOp::py_indptr() const {
-    Array<long> a(pyci_op_row_count(handle) + 1);
+    Array<long> a = pinned_long_array(pyci_op_row_count(handle) + 1);
     check(pyci_op_export_csr(handle, a.mutable_data(), nullptr, nullptr));
     return a;
 }

@@ -92,63 +92,12 @@ spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, c
     }
 }
 
-// The same rows with TRIPS x 64 entries of a row requested before the first x gather is waited for.  ncu of the kernel
-// above (profiles/r2l): 81 % of the warp samples wait on a long scoreboard -- a row is a chain of dependent latencies
-// (row pointer -> values / columns from HBM -> x from L2), and a row of 130..190 entries goes round that chain twice
-// with two trips in flight.  With three, rows up to 192 entries go round once.  Contiguous ranges only (chunk > 0); a
-// lane adds its products in the order spmv_short_rows does (trip by trip), so the sums are bit-identical.
-// (Measured and not kept: touching the next row of the warp with prefetch.global.L2 while the current one is
-// processed -- 2.007 ms against 2.017 ms on 5 M determinants: the HBM latency of the stream is not what the warps
-// wait for, the gathers are.)
-template<int TRIPS, int MINB>
-__global__ void __launch_bounds__(SPMV_BLOCK, MINB)
-spmv_short_rows_deep(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
-                     const double *__restrict__ x, double *__restrict__ y, long nrows, long chunk) {
-    const int lane = threadIdx.x & 31;
-    constexpr int NW = SPMV_BLOCK / 32;
-    const long row0 = (long)blockIdx.x * chunk;
-    const int nr = (int)(min(nrows, row0 + chunk) - row0); // rows of this CTA
-    const long *ip = indptr + row0;
-    for (int i = threadIdx.x >> 5; i < nr; i += NW) {
-        const long start = __ldg(ip + i);
-        const int len = (int)(__ldg(ip + i + 1) - start);
-        double acc0 = 0.0, acc1 = 0.0;
-        const int head = (int)(start & 1) && len > 0;
-        const double *vp = vals + start + head;
-        const int *cp = cols + start + head;
-        if (head && lane == 0)
-            acc0 = ld_stream_f64(vals + start) * __ldg(x + ld_stream_s32(cols + start));
-        const int nvec = (len - head) >> 1;
-        for (int q = lane; q < nvec; q += 32 * TRIPS) {
-            double2 v[TRIPS];
-            int2 c[TRIPS];
-#pragma unroll
-            for (int k = 0; k < TRIPS; ++k) {
-                // (slots beyond the row's end hold zeros and column 0: their products vanish)
-                v[k] = make_double2(0.0, 0.0);
-                c[k] = make_int2(0, 0);
-                if (q + 32 * k < nvec) {
-                    v[k] = ld_stream_f64x2(vp + 2 * (q + 32 * k));
-                    c[k] = ld_stream_s32x2(cp + 2 * (q + 32 * k));
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < TRIPS; ++k) {
-                const double xa = __ldg(x + c[k].x), xb = __ldg(x + c[k].y);
-                acc0 = fma(v[k].x, xa, acc0);
-                acc1 = fma(v[k].y, xb, acc1);
-            }
-        }
-        if (head + 2 * nvec < len && lane == 31)
-            acc1 = fma(ld_stream_f64(vp + 2 * nvec), __ldg(x + ld_stream_s32(cp + 2 * nvec)), acc1);
-        double acc = acc0 + acc1;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0)
-            y[row0 + i] = acc;
-    }
-}
+// Measured on the 5 M-determinant selected space (2.02 ms, 0.72 of the HBM peak; ncu: 81 % of the warp samples wait on
+// a long scoreboard, L1 hit rate of the gathers 59 %) and NOT kept -- none of them moves the number, the x gathers are
+// what the warps wait for: touching the warp's next row with prefetch.global.L2 (2.007 ms); three / four trips of a
+// row requested before the first gather at 40 / 46 registers (2.45 / 2.27 ms: the occupancy lost costs more); an L2
+// evict-first policy on the matrix stream so that x stays resident (2.021 ms; 1.006 -> 1.007 of peak on the long rows
+// of config 3, 0.904 -> 0.910 at config 4 on one GPU); the bulk-copy stream kernel below (3.9 ms).
 
 // TPR threads (a power of two, 32..256) stream one row; a CTA of 256 threads holds 256/TPR rows at a time.
 // Long rows use more threads per row: fewer rows are in flight, so the set of 2 MB pages being streamed
@@ -517,22 +466,9 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
             chunk = (chunk_env + 7) & ~7L;
             gg = (op->nloc + chunk - 1) / chunk;
         }
-        // PYCI_B200_SPMV_TRIPS=2/3/4: trips of a row requested up front (0: the two-trip kernel above)
-        static const int trips = getenv("PYCI_B200_SPMV_TRIPS") ? atoi(getenv("PYCI_B200_SPMV_TRIPS")) : 0;
-#define PYCI_SHORT_DEEP(T, B)                                                                                          \
-    spmv_short_rows_deep<T, B><<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, \
-                                                                             op->nloc, chunk)
-        if (chunk > 0 && trips == 2)
-            PYCI_SHORT_DEEP(2, 8);
-        else if (chunk > 0 && trips == 3)
-            PYCI_SHORT_DEEP(3, 6);
-        else if (chunk > 0 && trips == 4)
-            PYCI_SHORT_DEEP(4, 5);
-        else
-            spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev,
-                                                                          op->nloc, chunk);
+        spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc,
+                                                                      chunk);
         ctx->launches++;
-#undef PYCI_SHORT_DEEP
         PYCI_CUDA(cudaGetLastError());
         return PYCI_OK;
     }

@@ -232,6 +232,32 @@ def test_rectangular_like_reference(pyci):
     assert_csr(op, oi, ox, od)
 
 
+def test_row_pointer_results_own_their_recycled_buffers(pyci, monkeypatch):
+    """op.indptr() returns arrays over page-locked buffers that are recycled once numpy drops the array: an array that
+    is still alive keeps its contents when later calls run, outlives its operator, is writable like the reference's
+    copy, and equals what the pageable path returns."""
+    ham = pyci.hamiltonian(datafile("be_ccpvdz"))
+    wfn = pyci.fullci_wfn(ham.nbasis, 2, 2)
+    pyci.add_excitations(wfn, 0, 1, 2)
+    op = pyci.sparse_op(ham, wfn)
+    a = op.indptr()
+    keep = a.copy()
+    assert a.dtype == np.int64 and a.shape == (len(wfn) + 1,) and a.flags.c_contiguous and a.flags.writeable
+    b = op.indptr()
+    assert np.array_equal(a, b) and a.ctypes.data != b.ctypes.data
+    addr = b.ctypes.data
+    del b
+    small = pyci.sparse_op(ham, wfn, 7, symmetric=False).indptr()  # another size class: does not touch a's buffer
+    c = op.indptr()  # the buffer b gave back
+    assert c.ctypes.data == addr and np.array_equal(c, keep)
+    del op
+    assert np.array_equal(a, keep) and small.shape == (8,)
+    a[0] = 5  # the caller's array: writing it does not reach the library
+    monkeypatch.setenv("PYCI_B200_NO_PINNED_RESULTS", "1")
+    op2 = pyci.sparse_op(ham, wfn)
+    assert np.array_equal(op2.indptr(), keep)
+
+
 def test_update_after_adding_determinants(pyci):
     """HCI-style growth (sparseop.cpp:175-178): update(ham, wfn) after appending determinants gives the same
     operator as a fresh build."""
