@@ -210,6 +210,30 @@ def sparse_op(kind, nbasis, nocc_up, nocc_dn, dets, ints, nrow=-1, ncol=-1, symm
     return indptr, indices, data
 
 
+def sparse_op_updated(kind, nbasis, nocc_up, nocc_dn, dets, ints, nrow0, sizes, symmetric=True):
+    """Restates SparseOp::update (sparseop.cpp:175-201) applied after every growth of the wave function: the operator is
+    built with nrow0 rows and sizes[0] columns from the first sizes[0] determinants; update k appends the rows
+    [rows so far, sizes[k]) with ncol = sizes[k] and leaves the rows it already has untouched -- so a non-symmetric
+    operator keeps, in its old rows, only the columns those rows were built with.  dets is the final list (the wave
+    function only appends).  Returns (indptr, indices, data) of the operator after the last update."""
+    blocks, done = [(0, nrow0, sizes[0])], nrow0
+    for n in sizes[1:]:
+        blocks.append((done, n, n))
+        done = max(done, n)
+    ips, ixs, dvs, off = [np.zeros(1, dtype=np.int64)], [], [], 0
+    for lo, hi, ncol in blocks:
+        if hi <= lo:
+            continue
+        ip, ix, dv = sparse_op(kind, nbasis, nocc_up, nocc_dn, dets, ints, ncol=ncol, symmetric=symmetric,
+                               rows=np.arange(lo, hi, dtype=np.int64))
+        ips.append(ip[1:] + off)
+        ixs.append(ix)
+        dvs.append(dv)
+        off += int(ip[-1])
+    return (np.concatenate(ips), np.concatenate(ixs) if ixs else np.zeros(0, dtype=np.int64),
+            np.concatenate(dvs) if dvs else np.zeros(0))
+
+
 def matvec(indptr, indices, data, x, symmetric):
     """Restates SparseOp::perform_op / perform_op_symm (sparseop.cpp:96-112)."""
     nrow = len(indptr) - 1

@@ -591,8 +591,10 @@ int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn) {
     if (wfn->ndet < op->nrow)
         PYCI_FAIL(PYCI_ERR_VALUE, "the wave function holds fewer determinants (%ld) than the operator has rows (%ld)",
                   wfn->ndet, op->nrow);
-    if (!op->symmetric || op->nrow != op->ncol || ctx->nranks != 1 || op->foreign || wfn->nbasis > 64)
-        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "incremental update needs a square symmetric operator on one rank: rebuild instead");
+    // (row-sharded: the uniform row partition of the grown operator moves rows between ranks -- a rebuild; symmetric
+    // with nrow != ncol: the device rows hold columns the transposed entries cannot be told from)
+    if ((op->symmetric && op->nrow != op->ncol) || ctx->nranks != 1 || op->foreign || wfn->nbasis > 64)
+        PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "incremental update needs an operator on one rank (square if symmetric): rebuild instead");
     if (wfn->kind == PYCI_DOCI ? (!ham->h || !ham->v || !ham->w) : (!ham->one_mo || !ham->two_mo))
         PYCI_FAIL(PYCI_ERR_VALUE, "Hamiltonian lacks the integrals this wave-function kind needs");
     PYCI_TRY(ctx_activate(ctx));

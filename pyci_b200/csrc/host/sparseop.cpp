@@ -178,11 +178,14 @@ void SparseOp::build(const SQuantOp &ham, const Wfn &wfn, long rows, long cols) 
 }
 
 // SparseOp::py_update (sparseop.cpp:175-178): extend to all determinants now in wfn.  The reference appends rows
-// [old nrow, ndet) to its lower-triangular storage.  The device keeps full rows: pyci_op_update builds the new rows
-// and transposes their old-column entries into the old rows (only the new determinants are enumerated); operators
-// it does not cover (non-symmetric, rectangular, row-sharded) are rebuilt -- the exported CSR is identical.
+// [old nrow, ndet) to its storage and leaves the rows it has alone.  Symmetric: the device keeps full rows, so
+// pyci_op_update builds the new rows and transposes their old-column entries into the old rows (only the new
+// determinants are enumerated).  Non-symmetric: the new rows are appended, the old ones keep the columns they were
+// built with, like the reference's.  Row-sharded operators are rebuilt (the uniform partition moves rows between
+// ranks): identical for symmetric operators; a non-symmetric one then has complete rows where the reference has the
+// old ones.
 void SparseOp::update(const SQuantOp &ham, const Wfn &wfn) {
-    if (handle && symmetric && nrow == ncol && wfn.ndet >= nrow && pyci_ctx_nranks(device_context()) == 1) {
+    if (handle && (!symmetric || nrow == ncol) && wfn.ndet >= nrow && pyci_ctx_nranks(device_context()) == 1) {
         DeviceHam dham(ham);
         DeviceWfn dwfn(wfn);
         int rc;

@@ -1,4 +1,4 @@
-// Incremental growth of a symmetric operator: the device form of SparseOp::update
+// Incremental growth of an operator: the device form of SparseOp::update
 // (/root/reference/pyci/src/sparseop.cpp:175-201), which appends the rows of the determinants added to the wave
 // function since the operator was built (the step after add_hci in every selected-CI loop,
 // pyci/test/test_routines.py:450-453).
@@ -118,7 +118,115 @@ void release_op_arrays(pyci_op &t) {
 
 } // namespace
 
+// Non-symmetric operators.  The reference appends the rows [nrow, ndet) with ncol = ndet and leaves the rows it
+// already has as they are (sparseop.cpp:188-199): an old row keeps the columns it was built with and does not gain
+// the new determinants -- the grown operator has FEWER entries than a fresh non-symmetric build of the same wave
+// function (tests/golden/update.npz pins this against the compiled reference).  The device does the same: the new
+// rows are built with the ordinary construction and placed behind the old arrays; nothing old is touched.
+int op_append_rows_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op) {
+    cudaStream_t st = ctx->stream;
+    const long n0 = op->nrow, n1 = wfn->ndet, nnew = n1 - n0;
+    PYCI_CUDA(cudaEventRecord(ctx->ev[0], st));
+    pyci_op T;
+    T.ctx = ctx;
+    T.nrow = n1;
+    T.ncol = n1;
+    T.row0 = n0;
+    T.nloc = nnew;
+    T.npad = std::max<long>(nnew, 1);
+    T.symmetric = 0;
+    T.ecore = ham->ecore;
+    long *nip = nullptr;
+    int *ncols = nullptr, *nlow = nullptr;
+    double *nvals = nullptr, *ndiag = nullptr;
+    auto body = [&]() -> int {
+        if (nnew > 0) {
+            PYCI_CUDA(dev_malloc(&T.indptr, sizeof(long) * (size_t)(nnew + 1)));
+            PYCI_CUDA(dev_malloc(&T.lowcnt, sizeof(int) * (size_t)(nnew + 1)));
+            PYCI_CUDA(dev_malloc(&T.diag, sizeof(double) * (size_t)nnew));
+            PYCI_CUDA(cudaMemsetAsync(T.lowcnt, 0, sizeof(int) * (size_t)(nnew + 1), st));
+            PYCI_CUDA(cudaMemsetAsync(T.diag, 0, sizeof(double) * (size_t)nnew, st));
+            PYCI_TRY(op_build_impl(ctx, ham, wfn, &T));
+        }
+        const long old_total = op->nnz, total = old_total + T.nnz;
+        PYCI_CUDA(dev_malloc(&nip, sizeof(long) * (size_t)(n1 + 1)));
+        PYCI_CUDA(dev_malloc(&nvals, sizeof(double) * (size_t)(total + 4)));
+        PYCI_CUDA(dev_malloc(&ncols, sizeof(int) * (size_t)(total + 4)));
+        PYCI_CUDA(dev_malloc(&nlow, sizeof(int) * (size_t)(n1 + 1)));
+        PYCI_CUDA(dev_malloc(&ndiag, sizeof(double) * (size_t)std::max<long>(n1, 1)));
+        PYCI_CUDA(cudaMemcpyAsync(nip, op->indptr, sizeof(long) * (size_t)(n0 + 1), cudaMemcpyDeviceToDevice, st));
+        if (old_total > 0) {
+            PYCI_CUDA(cudaMemcpyAsync(ncols, op->cols, sizeof(int) * (size_t)old_total, cudaMemcpyDeviceToDevice, st));
+            PYCI_CUDA(cudaMemcpyAsync(nvals, op->vals, sizeof(double) * (size_t)old_total, cudaMemcpyDeviceToDevice, st));
+        }
+        if (n0 > 0) {
+            PYCI_CUDA(cudaMemcpyAsync(nlow, op->lowcnt, sizeof(int) * (size_t)n0, cudaMemcpyDeviceToDevice, st));
+            PYCI_CUDA(cudaMemcpyAsync(ndiag, op->diag, sizeof(double) * (size_t)n0, cudaMemcpyDeviceToDevice, st));
+        }
+        if (nnew > 0) {
+            if (T.nnz > 0) {
+                PYCI_CUDA(cudaMemcpyAsync(ncols + old_total, T.cols, sizeof(int) * (size_t)T.nnz, cudaMemcpyDeviceToDevice, st));
+                PYCI_CUDA(cudaMemcpyAsync(nvals + old_total, T.vals, sizeof(double) * (size_t)T.nnz, cudaMemcpyDeviceToDevice, st));
+            }
+            shift_indptr_kernel<<<(unsigned)((nnew + 256) / 256), 256, 0, st>>>(T.indptr, nnew, old_total, nip + n0);
+            ctx->launches++;
+            PYCI_CUDA(cudaMemcpyAsync(nlow + n0, T.lowcnt, sizeof(int) * (size_t)nnew, cudaMemcpyDeviceToDevice, st));
+            PYCI_CUDA(cudaMemcpyAsync(ndiag + n0, T.diag, sizeof(double) * (size_t)nnew, cudaMemcpyDeviceToDevice, st));
+            PYCI_CUDA(cudaGetLastError());
+        }
+        dev_free(op->indptr);
+        dev_free(op->cols);
+        dev_free(op->vals);
+        dev_free(op->lowcnt);
+        dev_free(op->diag);
+        dev_free(op->xbuf);
+        dev_free(op->ybuf);
+        dev_free(op->spmv_part);
+        op->indptr = nip;
+        op->cols = ncols;
+        op->vals = nvals;
+        op->lowcnt = nlow;
+        op->diag = ndiag;
+        nip = nullptr;
+        ncols = nlow = nullptr;
+        nvals = ndiag = nullptr;
+        op->xbuf = op->ybuf = nullptr;
+        op->spmv_part = nullptr;
+        op->spmv_part_n = 0;
+        op->spmv_tpr = 0;
+        op->nrow = op->ncol = n1;
+        op->row0 = 0;
+        op->nloc = n1;
+        op->npad = std::max<long>(1, n1);
+        op->nnz = total;
+        op->size_ref = total;
+        op->ecore = ham->ecore;
+        if (nnew > 0)
+            op->fill_kernel = T.fill_kernel;
+        return PYCI_OK;
+    };
+    const int rc = body();
+    release_op_arrays(T);
+    dev_free(nip);
+    dev_free(ncols);
+    dev_free(nvals);
+    dev_free(nlow);
+    dev_free(ndiag);
+    PYCI_TRY(rc);
+    PYCI_CUDA(cudaEventRecord(ctx->ev[1], st));
+    PYCI_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    op->times[0] = wfn->hash_seconds;
+    op->times[1] = T.times[1];
+    op->times[2] = T.times[2];
+    op->times[3] = ms * 1e-3;
+    return PYCI_OK;
+}
+
 int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op) {
+    if (!op->symmetric)
+        return op_append_rows_impl(ctx, ham, wfn, op);
     cudaStream_t st = ctx->stream;
     const long n0 = op->nrow, n1 = wfn->ndet;
     if (n1 == n0)

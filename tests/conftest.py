@@ -91,3 +91,15 @@ def trdm_golden():
 
 TRDM_CASES = [("h6_fullci", "fullci", 6, (3, 3)), ("lih_fullci", "fullci", 6, (2, 1)), ("be_doci", "doci", 14, (2, 2)),
               ("h4_fullci", "fullci", 4, (2, 2))]
+
+
+@pytest.fixture(scope="session")
+def update_golden():
+    """SparseOp::update applied by the compiled reference (tests/golden/make_golden_update.py)."""
+    with np.load(os.path.join(GOLDEN, "update.npz")) as f:
+        return {k: f[k] for k in f.files}
+
+
+UPDATE_CASES = [("be.fullci22", "be_ccpvdz", "fullci", (2, 2)), ("be.doci22", "be_ccpvdz", "doci", (2, 2))]
+UPDATE_MODES = [("sym", True), ("nonsym", False), ("rect", False)]
+

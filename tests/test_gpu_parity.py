@@ -607,15 +607,66 @@ def test_incremental_update_equals_fresh_build(pyci, kind, n, occ):
         wfn.close()
     # operators the incremental path does not cover are refused (the host class rebuilds them)
     wfn = cabi.Wfn(ctx, ckind, n, occ[0], occ[1], alld[:900])
-    rect = cabi.Op(ctx, ham, wfn, nrow=800, ncol=900, symmetric=False)
+    rect = cabi.Op(ctx, ham, wfn, nrow=800, ncol=900, symmetric=True)
     with pytest.raises(cabi.PyciError) as ei:
         rect.update(ham, wfn)
     assert ei.value.status == cabi.ERR_UNSUPPORTED
+    rect.close()
+    # a non-symmetric operator grows like the reference's: rows appended, old rows keep the columns they were built with
+    rect = cabi.Op(ctx, ham, wfn, nrow=800, ncol=900, symmetric=False)
+    rect.update(ham, wfn)  # same wave function: rows 800..899 appear, all 900 columns
+    wfn.close()
+    wfn = cabi.Wfn(ctx, ckind, n, occ[0], occ[1], alld[:1500])
+    rect.update(ham, wfn)
+    rect.update(ham, wfn)  # nothing to add
+    oi, ox, od = O.sparse_op_updated(okind, n, occ[0], occ[1], alld[:1500], ints, 800, [900, 900, 1500], symmetric=False)
+    a = rect.export_csr()
+    assert (rect.nrow, rect.ncol, rect.size) == (1500, 1500, len(ox))
+    assert np.array_equal(a[0], oi) and np.array_equal(a[1], ox) and np.array_equal(a[2], od)
+    y = rect.matvec(x[:1500])
+    np.testing.assert_allclose(y, O.matvec(oi, ox, od, x[:1500], False), rtol=0, atol=1e-11)
+    assert rect.get_element(10, 1400) == 0.0  # an old row never gained the new columns
     rect.close()
     wfn.close()
     op.close()
     ham.close()
     ctx.close()
+
+
+from conftest import UPDATE_CASES, UPDATE_MODES  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,fn,kind,occ", UPDATE_CASES)
+@pytest.mark.parametrize("mode,symm", UPDATE_MODES)
+def test_update_like_the_compiled_reference(pyci, update_golden, tag, fn, kind, occ, mode, symm):
+    """op.update(ham, wfn) through the host module, the calls of tests/golden/make_golden_update.py: the operator after
+    two growth steps equals the compiled reference's -- symmetric (rows appended to the lower triangle), non-symmetric
+    and rectangular non-symmetric (old rows keep their columns)."""
+    g, key = update_golden, "%s.%s" % (tag, mode)
+    ham = pyci.hamiltonian(datafile(fn))
+    wfn = getattr(pyci, kind + "_wfn")(ham.nbasis, *occ)
+    levels = {"fullci": [(0, 1), (2,), (3,)], "doci": [(0, 1), (2,)]}[kind]
+    pyci.add_excitations(wfn, *levels[0])
+    sizes, nrow0 = g[key + ".sizes"].tolist(), int(g[key + ".nrow0"])
+    assert len(wfn) == sizes[0]
+    op = pyci.sparse_op(ham, wfn, nrow0, len(wfn), symmetric=symm)
+    for k, lv in enumerate(levels[1:], 1):
+        pyci.add_excitations(wfn, *lv)
+        assert len(wfn) == sizes[k]
+        op.update(ham, wfn)
+    assert np.array_equal(wfn.to_det_array(), g[key + ".dets"])
+    assert op.shape == tuple(g[key + ".shape"]) and op.size == int(g[key + ".nnz"])
+    assert np.array_equal(op.indptr(), g[key + ".indptr"])
+    assert sha(op.indices()) == str(g[key + ".indices.sha256"]) and sha(op.data()) == str(g[key + ".data.sha256"])
+    if symm:
+        es, _ = op.solve(n=1, tol=1e-9)
+        fresh = pyci.sparse_op(ham, wfn)
+        ef, _ = fresh.solve(n=1, tol=1e-9)
+        assert abs(es[0] - ef[0]) <= E_ATOL
+    else:
+        xx = seeded_vec(len(wfn), 4)
+        ip, ix, dv = op.indptr(), op.indices(), op.data()
+        np.testing.assert_allclose(op(xx), O.matvec(ip, ix, dv, xx, False), rtol=0, atol=1e-11)
 
 
 # ---- compute_transition_rdms / compute_overlap (rdm.cpp:634-1009, overlap.cpp) ---------------------------

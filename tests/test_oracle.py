@@ -262,3 +262,27 @@ def test_oracle_hci_enpt2_limits():
             if v != 0.0 and tuple(full[j].reshape(-1).tolist()) not in have:
                 connected.add(tuple(full[j].reshape(-1).tolist()))
     assert new == connected
+
+
+from conftest import UPDATE_CASES, UPDATE_MODES  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,fn,kind,occ", UPDATE_CASES)
+@pytest.mark.parametrize("mode,symm", UPDATE_MODES)
+def test_oracle_update_equals_reference(update_golden, tag, fn, kind, occ, mode, symm):
+    """SparseOp::update (sparseop.cpp:175-201) as the compiled reference applies it, twice in a row: appended rows see
+    the grown wave function, rows the operator already has are left alone -- for a non-symmetric operator they keep
+    the columns they were built with (fewer entries than a fresh build has)."""
+    g, key = update_golden, "%s.%s" % (tag, mode)
+    ecore, one, two = O.read_fcidump(datafile(fn))
+    ints = O.senzero_integrals(one, two) if kind == "doci" else (one, two)
+    okind = {"doci": O.DOCI, "fullci": O.FULLCI}[kind]
+    dets, sizes, nrow0 = g[key + ".dets"], g[key + ".sizes"].tolist(), int(g[key + ".nrow0"])
+    ip, ix, dv = O.sparse_op_updated(okind, one.shape[0], occ[0], occ[1], dets, ints, nrow0, sizes, symm)
+    assert tuple(g[key + ".shape"]) == (sizes[-1], sizes[-1]) and len(ix) == int(g[key + ".nnz"])
+    assert np.array_equal(ip, g[key + ".indptr"])
+    assert sha(ix) == str(g[key + ".indices.sha256"]) and sha(dv) == str(g[key + ".data.sha256"])
+    if not symm:  # the point of the non-symmetric cases: not what a fresh build gives
+        fresh = O.sparse_op(okind, one.shape[0], occ[0], occ[1], dets, ints, symmetric=False)
+        assert len(fresh[1]) > len(ix)
+
