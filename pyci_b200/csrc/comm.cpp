@@ -19,6 +19,7 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -53,6 +54,7 @@ NcclApi &api() {
         LOAD(CommDestroy)
         LOAD(AllGather)
         LOAD(AllReduce)
+        LOAD(Broadcast)
         LOAD(Send)
         LOAD(Recv)
         LOAD(GroupStart)
@@ -124,6 +126,31 @@ int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, 
     return PYCI_OK;
 }
 
+// All-gather of unequal shards: rank p contributes bounds[p+1] - bounds[p] elements, which land at recv + bounds[p] on
+// every rank (the nnz-balanced row partition of a selected space).  One NCCL group of broadcasts, one per rank.
+int comm_allgatherv_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, const long *bounds) {
+    const int R = ctx->nranks, me = ctx->rank;
+    if (R == 1) {
+        if (send_dev != recv_dev && bounds[1] > bounds[0])
+            PYCI_CUDA(cudaMemcpyAsync(recv_dev + bounds[0], send_dev, sizeof(double) * (size_t)(bounds[1] - bounds[0]),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        return PYCI_OK;
+    }
+    PYCI_NCCL(api().GroupStart());
+    ncclResult_t r = ncclSuccess;
+    for (int p = 0; p < R && r == ncclSuccess; ++p) {
+        const long cnt = bounds[p + 1] - bounds[p];
+        if (cnt <= 0)
+            continue;
+        r = api().Broadcast(p == me ? (const void *)send_dev : (const void *)(recv_dev + bounds[p]), recv_dev + bounds[p],
+                            (size_t)cnt, ncclDouble, p, (ncclComm_t)ctx->comm, ctx->stream);
+    }
+    const ncclResult_t g = api().GroupEnd();
+    PYCI_NCCL(r);
+    PYCI_NCCL(g);
+    return PYCI_OK;
+}
+
 int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count) {
     if (ctx->nranks == 1)
         return PYCI_OK;
@@ -171,6 +198,32 @@ int comm_alltoallv_u64(pyci_ctx *ctx, const unsigned long long *send, const long
             r = api().Send(send + soff[p], (size_t)scount[p], ncclUint64, p, (ncclComm_t)ctx->comm, ctx->stream);
         if (r == ncclSuccess && rcount[p] > 0)
             r = api().Recv(recv + roff[p], (size_t)rcount[p], ncclUint64, p, (ncclComm_t)ctx->comm, ctx->stream);
+    }
+    const ncclResult_t g = api().GroupEnd();
+    PYCI_NCCL(r);
+    PYCI_NCCL(g);
+    return PYCI_OK;
+}
+
+// The same exchange in bytes (arrays of 4-byte columns, 8-byte values, ...): counts and offsets are byte counts.
+int comm_alltoallv_bytes(pyci_ctx *ctx, const void *send, const long *scount, const long *soff, void *recv,
+                         const long *rcount, const long *roff) {
+    const int R = ctx->nranks, me = ctx->rank;
+    const char *s = static_cast<const char *>(send);
+    char *d = static_cast<char *>(recv);
+    if (scount[me] > 0)
+        PYCI_CUDA(cudaMemcpyAsync(d + roff[me], s + soff[me], (size_t)scount[me], cudaMemcpyDeviceToDevice, ctx->stream));
+    if (R == 1)
+        return PYCI_OK;
+    PYCI_NCCL(api().GroupStart());
+    ncclResult_t r = ncclSuccess;
+    for (int p = 0; p < R && r == ncclSuccess; ++p) {
+        if (p == me)
+            continue;
+        if (scount[p] > 0)
+            r = api().Send(s + soff[p], (size_t)scount[p], ncclChar, p, (ncclComm_t)ctx->comm, ctx->stream);
+        if (r == ncclSuccess && rcount[p] > 0)
+            r = api().Recv(d + roff[p], (size_t)rcount[p], ncclChar, p, (ncclComm_t)ctx->comm, ctx->stream);
     }
     const ncclResult_t g = api().GroupEnd();
     PYCI_NCCL(r);

@@ -117,7 +117,10 @@ struct pyci_op {
     pyci_ctx *ctx = nullptr;
     long nrow = 0, ncol = 0; // global shape
     long row0 = 0, nloc = 0; // this rank's rows [row0, row0+nloc)
-    long npad = 0;           // rows per rank (uniform), npad*nranks >= nrow
+    long npad = 0;           // stride of a rank's vectors: rows per rank of the uniform partition, npad*nranks >= nrow
+                             // (nnz-balanced partition: the largest row count of any rank)
+    std::vector<long> bounds; // nnz-balanced partition (rebalance.cu): rank p holds rows [bounds[p], bounds[p+1]);
+                              // empty = uniform blocks of npad rows
     int symmetric = 0;
     bool foreign = false;    // built by pyci_op_build_shard for a rank layout other than the context's: no collectives
     double ecore = 0.0;
@@ -162,6 +165,9 @@ int comm_unique_id(void *out128);
 int comm_init(pyci_ctx *ctx, int rank, int nranks, const void *id128);
 void comm_destroy(pyci_ctx *ctx);
 int comm_allgather_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, long count_per_rank);
+int comm_allgatherv_f64(pyci_ctx *ctx, const double *send_dev, double *recv_dev, const long *bounds);
+int comm_alltoallv_bytes(pyci_ctx *ctx, const void *send, const long *scount, const long *soff, void *recv,
+                         const long *rcount, const long *roff);
 int comm_allreduce_sum_f64(pyci_ctx *ctx, double *buf_dev, long count);
 int comm_allreduce_sum_i64_host(pyci_ctx *ctx, long *vals, int count);
 int comm_alltoallv_u64(pyci_ctx *ctx, const unsigned long long *send, const long *scount, const long *soff,
@@ -180,6 +186,10 @@ int op_build_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_
 int scan_counts(pyci_ctx *ctx, const int *cnt, long n, long *indptr, int *maxcnt);
 // update.cu
 int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci_op *op);
+// rebalance.cu: moves rows between neighbouring ranks so that every rank stores the same number of entries (collective)
+int op_rebalance(pyci_ctx *ctx, pyci_op *op);
+// every rank's shard of a row-distributed vector, concatenated in row order, on every rank
+int op_allgather_rows(pyci_ctx *ctx, const pyci_op *op, const double *send_dev, double *recv_dev);
 // spmv.cu
 int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev);
 // solver.cu
