@@ -557,6 +557,9 @@ static int op_build_common(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *w
         cudaMemsetAsync(op->diag, 0, sizeof(double) * (size_t)op->npad, ctx->stream);
         rc = op_build_impl(ctx, ham, wfn, op);
     }
+    // selected spaces: equal stored entries per rank instead of equal rows (rebalance.cu; collective)
+    if (rc == PYCI_OK && !foreign && ctx->nranks > 1)
+        rc = op_rebalance(ctx, op);
     if (rc != PYCI_OK) {
         pyci_op_destroy(op);
         return rc;
@@ -786,7 +789,7 @@ int pyci_op_matvec(pyci_op *op, const double *x, double *y) {
     PYCI_TRY(spmv_launch(op, op->xbuf, yloc));
     const double *ysrc = yloc;
     if (R > 1) {
-        PYCI_TRY(comm_allgather_f64(ctx, yloc, op->ybuf, op->npad));
+        PYCI_TRY(op_allgather_rows(ctx, op, yloc, op->ybuf));
         ysrc = op->ybuf;
     }
     PYCI_CUDA(cudaMemcpyAsync(y, ysrc, sizeof(double) * op->nrow, cudaMemcpyDeviceToHost, ctx->stream));

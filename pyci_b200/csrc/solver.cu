@@ -275,7 +275,7 @@ struct Solver {
         const double *xin = v;
         if (R > 1) {
             PYCI_NVTX("pyci:allgather(trial vector)");
-            PYCI_TRY(comm_allgather_f64(ctx, v, xfull, ld));
+            PYCI_TRY(op_allgather_rows(ctx, op, v, xfull));
             xin = xfull;
         }
         PYCI_TRY(spmv_launch(op, xin, w));
@@ -459,7 +459,7 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     {
         const double *dsrc = op->diag;
         if (R > 1) {
-            PYCI_TRY(comm_allgather_f64(ctx, op->diag, S.xfull, S.ld));
+            PYCI_TRY(op_allgather_rows(ctx, op, op->diag, S.xfull));
             dsrc = S.xfull;
         }
         PYCI_CUDA(cudaMemcpyAsync(hdiag.data(), dsrc, vec * R, cudaMemcpyDeviceToHost, S.st));
@@ -657,7 +657,7 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     for (int r = 0; r < nroot; ++r) {
         const double *src = S.X + (size_t)r * S.ld;
         if (R > 1) {
-            PYCI_TRY(comm_allgather_f64(ctx, src, S.xfull, S.ld));
+            PYCI_TRY(op_allgather_rows(ctx, op, src, S.xfull));
             src = S.xfull;
         }
         PYCI_CUDA(cudaMemcpyAsync(evecs + (size_t)r * nrow, src, sizeof(double) * nrow, cudaMemcpyDeviceToHost, S.st));

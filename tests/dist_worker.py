@@ -72,6 +72,33 @@ e2, _ = op2.solve(n=1, tol=1e-9)
 ip2, ix2, dv2 = O.sparse_op(O.FULLCI, n, occ[0], occ[1], sel.to_det_array(), (s1, s2))
 e2o, _ = O.lowest_eigenpair(ip2, ix2, dv2, len(sel))
 assert abs(e2[0] - e2o) < 1e-9, (e2, e2o)
+# ---- nnz-balanced row partition (rebalance.cu): the grown space has long rows first (the determinants the selection
+# started from) and short ones behind; any imbalance is evened out here (PYCI_B200_REBALANCE_MIN=1)
+os.environ["PYCI_B200_REBALANCE_MIN"] = "1.0"
+op3 = pyci.sparse_op(hams, sel)
+del os.environ["PYCI_B200_REBALANCE_MIN"]
+st2, st3 = op2.stats(), op3.stats()
+parts = [None] * world
+dist.all_gather_object(parts, (st2["stored_nnz"], st3["row_begin"], st3["row_count"], st3["stored_nnz"]))
+assert parts[0][1] == 0 and sum(p[2] for p in parts) == len(sel)
+assert all(parts[k][1] + parts[k][2] == parts[k + 1][1] for k in range(world - 1))  # contiguous, in rank order
+assert sum(p[3] for p in parts) == sum(p[0] for p in parts)
+uniform_worst, balanced_worst = max(p[0] for p in parts), max(p[3] for p in parts)
+longest_row = int(np.max(np.diff(ip2))) * 2
+assert balanced_worst <= uniform_worst and balanced_worst <= sum(p[3] for p in parts) / world + longest_row, parts
+lo3, cnt3 = st3["row_begin"], st3["row_count"]
+assert np.array_equal(op3.indptr(), ip2[lo3:lo3 + cnt3 + 1] - ip2[lo3])
+assert np.array_equal(op3.indices(), ix2[ip2[lo3]:ip2[lo3 + cnt3]])
+assert np.array_equal(op3.data(), dv2[ip2[lo3]:ip2[lo3 + cnt3]])
+x3 = seeded_vec(len(sel), 8)
+y3, y3o = op3(x3), O.matvec(ip2, ix2, dv2, x3, True)
+assert np.max(np.abs(y3 - y3o)) <= 1e-11 * np.max(np.abs(y3o))
+e3, c3 = op3.solve(n=2, tol=1e-9)
+assert abs(e3[0] - e2o) < 1e-9 and c3.shape == (2, len(sel)), (e3, e2o)
+r3 = op3(c3[0]) - (e3[0] - 0.0) * c3[0]
+assert np.linalg.norm(r3) < 1e-6
+if rank == 0:
+    print("rebalance: worst rank %d -> %d stored entries of %d" % (uniform_worst, balanced_worst, sum(p[3] for p in parts)), flush=True)
 # ---- selected GenCI space through the segment-pair join (join.cuh), row-sharded: this rank's rows x all determinants
 os.environ["PYCI_B200_FORCE_JOIN"] = "1"
 ng, og = 16, 5
@@ -82,7 +109,8 @@ gw = pyci.genci_wfn(ng, og, 0, gd)
 gh = pyci.hamiltonian(0.0, g1, g2)
 opg = pyci.sparse_op(gh, gw)
 gi, gx, gv = O.sparse_op(O.GENCI, ng, og, 0, gd, (g1, g2))
-lo, cnt = row_partition(len(gd), len(gd), world)[rank]
+stg = opg.stats()  # (a selected space may have been re-partitioned to equal stored entries per rank)
+lo, cnt = stg["row_begin"], stg["row_count"]
 assert np.array_equal(opg.indptr(), gi[lo:lo + cnt + 1] - gi[lo])
 assert np.array_equal(opg.indices(), gx[gi[lo]:gi[lo + cnt]])
 assert np.array_equal(opg.data(), gv[gi[lo]:gi[lo + cnt]])
