@@ -19,7 +19,9 @@ def env_ranks():
 
 def row_partition(nrow, ncol, nranks):
     """[(row_begin, row_count)] per rank: uniform blocks of ``npad = ceil(max(nrow, ncol) / nranks)`` rows,
-    the same rule as pyci_op_build (pyci_b200/csrc/api.cu) so that the all-gathered vector is rank-major."""
+    the rule pyci_op_build (pyci_b200/csrc/api.cu) builds with.  A selected space may then be re-partitioned to equal
+    stored entries per rank (pyci_b200/csrc/rebalance.cu): ``op.stats()["row_begin"/"row_count"]`` is what a rank
+    holds."""
     npad = max(1, -(-max(nrow, ncol) // nranks))
     out = []
     for r in range(nranks):
