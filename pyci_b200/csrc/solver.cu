@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(RB) multi_dot_kernel(const double *__restrict_
     }
 }
 
-// x[i] = beta*x[i] + alpha * sum_j s[j] V[j*ld+i]
+// y[i] = beta*x[i] + alpha * sum_j s[j] V[j*ld+i]   (y may be x)
 __global__ void __launch_bounds__(RB) combine_kernel(const double *__restrict__ V, long ld, int k,
                                                      const double *__restrict__ s, double alpha, double beta,
-                                                     double *__restrict__ x, long n) {
+                                                     const double *x, double *y, long n) {
     extern __shared__ double sh[];
     for (int j = threadIdx.x; j < k; j += RB)
         sh[j] = s[j];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(RB) combine_kernel(const double *__restrict__ 
         double a = 0.0;
         for (int j = 0; j < k; ++j)
             a = fma(sh[j], V[j * ld + i], a);
-        x[i] = (beta == 0.0 ? 0.0 : beta * x[i]) + alpha * a;
+        y[i] = (beta == 0.0 ? 0.0 : beta * x[i]) + alpha * a;
     }
 }
 
@@ -343,14 +343,14 @@ struct Solver {
         return d;
     }
 
-    // x = beta x + alpha * sum_j s_j Vb_j   (asynchronous)
-    int combine(const double *Vb, int k, const double *s_host, double alpha, double beta, double *x) {
+    // y = beta x + alpha * sum_j s_j Vb_j   (asynchronous; y = nullptr: in place)
+    int combine(const double *Vb, int k, const double *s_host, double alpha, double beta, double *x, double *y = nullptr) {
         if (k > small_cap)
             PYCI_FAIL(PYCI_ERR_RUNTIME, "subspace larger than scratch");
         int err;
         const double *d = stage(s_host, k, &err);
         PYCI_TRY(err);
-        combine_kernel<<<grid, RB, sizeof(double) * (size_t)(k + 2), st>>>(Vb, ld, k, d, alpha, beta, x, nloc);
+        combine_kernel<<<grid, RB, sizeof(double) * (size_t)(k + 2), st>>>(Vb, ld, k, d, alpha, beta, x, y ? y : x, nloc);
         ctx->launches++;
         return PYCI_OK;
     }
@@ -359,9 +359,16 @@ struct Solver {
     // of dot products, [V_0..V_{m-1}, t] . t, i.e. one reduction and one synchronisation; V is orthonormal, so
     // the norm after the second pass is |t|^2 - sum_j (V_j . t)^2 and the scaling rides on the second update.
     // *rel = norm of the orthogonal component relative to the input norm.
-    int orthonormalize(double *t, int m, std::vector<double> &tmp, double *rel) {
+    // "Twice is enough", and once is when little was removed (Daniel-Gragg-Kaufman-Stewart): if the first pass leaves
+    // more than 1/sqrt(2) of the vector, what rounding puts back along V is at the level of the unit round-off and the
+    // second pass -- a second reading of the whole basis -- is skipped; the scaling then rides on the first update.
+    // (On short-row operators the basis passes of a Davidson step are a third of its time: config 5.)
+    // dst != nullptr: the orthonormal vector is written there (the next basis vector's place) by the last update
+    // instead of being copied afterwards; t is then scratch.
+    int orthonormalize(double *t, int m, std::vector<double> &tmp, double *rel, double *dst = nullptr) {
         tmp.resize((size_t)m + 1);
         double n0 = 0.0, n1 = 0.0;
+        static const bool dgks = getenv("PYCI_B200_SOLVER_GS2") == nullptr;
         for (int pass = 0; pass < 2; ++pass) {
             // t sits at V + m * ld when it is the next basis vector; in general it is a separate buffer: two batches
             if (m > 0)
@@ -375,8 +382,19 @@ struct Solver {
                     *rel = 0.0;
                     return PYCI_OK;
                 }
-                if (m > 0)
+                if (m > 0) {
+                    double proj = 0.0;
+                    for (int j = 0; j < m; ++j)
+                        proj += tmp[(size_t)j] * tmp[(size_t)j];
+                    const double left = n0 - proj;
+                    if (dgks && left > 0.5 * n0) {
+                        const double inv = 1.0 / std::sqrt(left);
+                        PYCI_TRY(combine(V, m, tmp.data(), -inv, inv, t, dst));
+                        *rel = std::sqrt(left / n0);
+                        return PYCI_OK;
+                    }
                     PYCI_TRY(combine(V, m, tmp.data(), -1.0, 1.0, t));
+                }
             } else {
                 double proj = 0.0;
                 for (int j = 0; j < m; ++j)
@@ -388,10 +406,12 @@ struct Solver {
                 }
                 const double inv = 1.0 / std::sqrt(n1);
                 if (m > 0) {
-                    PYCI_TRY(combine(V, m, tmp.data(), -inv, inv, t));
+                    PYCI_TRY(combine(V, m, tmp.data(), -inv, inv, t, dst));
                 } else {
                     scale_kernel<<<grid, RB, 0, st>>>(t, inv, nloc);
                     ctx->launches++;
+                    if (dst)
+                        PYCI_CUDA(cudaMemcpyAsync(dst, t, sizeof(double) * (size_t)ld, cudaMemcpyDeviceToDevice, st));
                 }
             }
         }
@@ -408,8 +428,18 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     pyci_ctx *ctx = op->ctx;
     const long nrow = op->nrow;
     const int R = ctx->nranks;
-    if (ncv == -1)
-        ncv = std::min(nrow, std::max(2 * n + 1, 20L));
+    // ncv = -1: the reference's default is max(2 n + 1, 20) Lanczos vectors (sparseop.cpp:129-130).  A Davidson step
+    // reads its basis about five times (projection, Ritz vector + residual, orthogonalisation), which is free beside
+    // a product over rows of thousands of entries and a third of the step over rows of ~200 (config 5): there the
+    // thick restart converges in the same number of products with half the basis (5 M determinants, rows of 158:
+    // 516 / 479 / 489 / 482 / 533 products and 1.63 / 1.46 / 1.43 / 1.38 / 1.48 s at 20 / 16 / 12 / 10 / 8 vectors).
+    if (ncv == -1) {
+        long tot[2] = {op->nnz, op->nloc}; // (the same decision on every rank: the ranks' rows differ in length)
+        if (R > 1)
+            PYCI_TRY(comm_allreduce_sum_i64_host(ctx, tot, 2));
+        const long avg_row = tot[0] / std::max<long>(tot[1], 1);
+        ncv = std::min(nrow, avg_row < 512 ? std::max(3 * n + 7, 10L) : std::max(2 * n + 1, 20L));
+    }
     if (maxiter == -1)
         maxiter = n * nrow * 10;
     if (ncv <= n || ncv > nrow)
@@ -613,10 +643,9 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
                 ctx->launches++;
             }
             double rel = 0.0;
-            PYCI_TRY(S.orthonormalize(t, m, tmp, &rel));
+            PYCI_TRY(S.orthonormalize(t, m, tmp, &rel, S.V + (size_t)m * S.ld)); // lands in the next basis slot
             if (rel < 1.0e-10)
                 continue; // correction already in the subspace
-            PYCI_CUDA(cudaMemcpyAsync(S.V + (size_t)m * S.ld, t, vec, cudaMemcpyDeviceToDevice, S.st));
             ++m;
             ++nnew;
         }
