@@ -574,7 +574,7 @@ def measure_case(B, spec, steps, warmup, gate_target=1000, rdm=False, clocks=Fal
     fill_bytes = op.stored_nnz * 12 + (op.row_count + 1) * 8 + op.row_count * (16 if kind == cabi.FULLCI else 8)
     fill_gbs = fill_bytes / max(fill_kernel_s, 1e-9) / 1e9
     fill_name, count_name = op.fill_kernel(), op.count_kernel()
-    spmv_name = "spmv_rows" if spmv_bytes / max(op.row_count, 1) > 12 * 320 else "spmv_short_rows"
+    spmv_name = "spmv_rows" if spmv_bytes / max(op.row_count, 1) > 12 * 320 else "spmv_short_rows_seq"
     op_bytes = spmv_bytes
 
     # ---- time to E0: one more construction + the Davidson solve, device-timed

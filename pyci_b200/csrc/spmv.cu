@@ -92,6 +92,53 @@ spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, c
     }
 }
 
+// The same rows with lane l of a trip on entry 32 k + l (scalar loads) instead of on the pair (2q, 2q + 1).  ncu of the
+// kernel above (profiles/r2v): the L1 data pipe is what is full -- l1tex__data_pipe_lsu_wavefronts at 85 % of its
+// peak, ~17 wavefronts per gather instruction -- not HBM (58 %) and not the issue slots (42 %).  The columns of a row
+// ascend, and in a selected space 31 % of neighbouring entries gather from the same 128-byte line of x (14 % from the
+// same sector): with the pair mapping the two fall into different gather instructions (x of the even entries, then x
+// of the odd ones); here neighbouring entries sit in neighbouring lanes of ONE instruction and share its wavefront.
+// TRIPS x 32 entries of a row are requested before the first gather is waited for.
+template<int TRIPS>
+__global__ void __launch_bounds__(SPMV_BLOCK, 8)
+spmv_short_rows_seq(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
+                    const double *__restrict__ x, double *__restrict__ y, long nrows, long chunk) {
+    const int lane = threadIdx.x & 31;
+    constexpr int NW = SPMV_BLOCK / 32;
+    const long row0 = (long)blockIdx.x * chunk;
+    const int nr = (int)(min(nrows, row0 + chunk) - row0); // rows of this CTA
+    const long *ip = indptr + row0;
+    for (int i = threadIdx.x >> 5; i < nr; i += NW) {
+        const long start = __ldg(ip + i);
+        const int len = (int)(__ldg(ip + i + 1) - start);
+        const double *vp = vals + start;
+        const int *cp = cols + start;
+        double acc = 0.0;
+        for (int e = lane; e < len; e += 32 * TRIPS) {
+            double v[TRIPS];
+            int c[TRIPS];
+#pragma unroll
+            for (int k = 0; k < TRIPS; ++k) {
+                // (slots beyond the row's end hold zero and column 0: their products vanish)
+                v[k] = 0.0;
+                c[k] = 0;
+                if (e + 32 * k < len) {
+                    v[k] = ld_stream_f64(vp + e + 32 * k);
+                    c[k] = ld_stream_s32(cp + e + 32 * k);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TRIPS; ++k)
+                acc = fma(v[k], __ldg(x + c[k]), acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0)
+            y[row0 + i] = acc;
+    }
+}
+
 // Measured on the 5 M-determinant selected space (2.02 ms, 0.72 of the HBM peak; ncu: 81 % of the warp samples wait on
 // a long scoreboard, L1 hit rate of the gathers 59 %) and NOT kept -- none of them moves the number, the x gathers are
 // what the warps wait for: touching the warp's next row with prefetch.global.L2 (2.007 ms); three / four trips of a
@@ -466,7 +513,15 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
             chunk = (chunk_env + 7) & ~7L;
             gg = (op->nloc + chunk - 1) / chunk;
         }
-        spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc,
+        // the entry-per-lane kernel (contiguous ranges only); PYCI_B200_SPMV_SEQ=0: the pair-per-lane kernel.  5 M
+        // determinants: 2.013 ms -> 1.752 ms = 0.835 of the HBM peak; 1 / 2 / 3 trips in flight are within 1 %, 4 and 6
+        // spill and lose (1.92 / 2.12 ms)
+        static const bool seq = !(getenv("PYCI_B200_SPMV_SEQ") && atoi(getenv("PYCI_B200_SPMV_SEQ")) == 0);
+        if (chunk > 0 && seq)
+            spmv_short_rows_seq<2><<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev,
+                                                                                 op->nloc, chunk);
+        else
+            spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc,
                                                                       chunk);
         ctx->launches++;
         PYCI_CUDA(cudaGetLastError());
