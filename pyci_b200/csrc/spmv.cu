@@ -99,8 +99,8 @@ spmv_short_rows(const long *__restrict__ indptr, const int *__restrict__ cols, c
 // same sector): with the pair mapping the two fall into different gather instructions (x of the even entries, then x
 // of the odd ones); here neighbouring entries sit in neighbouring lanes of ONE instruction and share its wavefront.
 // TRIPS x 32 entries of a row are requested before the first gather is waited for.
-template<int TRIPS>
-__global__ void __launch_bounds__(SPMV_BLOCK, 8)
+template<int TRIPS, int MINB>
+__global__ void __launch_bounds__(SPMV_BLOCK, MINB)
 spmv_short_rows_seq(const long *__restrict__ indptr, const int *__restrict__ cols, const double *__restrict__ vals,
                     const double *__restrict__ x, double *__restrict__ y, long nrows, long chunk) {
     const int lane = threadIdx.x & 31;
@@ -516,13 +516,24 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
         // the entry-per-lane kernel (contiguous ranges only); PYCI_B200_SPMV_SEQ=0: the pair-per-lane kernel.  5 M
         // determinants: 2.013 ms -> 1.752 ms = 0.835 of the HBM peak; 1 / 2 / 3 trips in flight are within 1 %, 4 and 6
         // spill and lose (1.92 / 2.12 ms)
-        static const bool seq = !(getenv("PYCI_B200_SPMV_SEQ") && atoi(getenv("PYCI_B200_SPMV_SEQ")) == 0);
-        if (chunk > 0 && seq)
-            spmv_short_rows_seq<2><<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev,
-                                                                                 op->nloc, chunk);
+        static const int seq = getenv("PYCI_B200_SPMV_SEQ") ? atoi(getenv("PYCI_B200_SPMV_SEQ")) : 2;
+#define PYCI_SEQ(T, B)                                                                                              \
+    spmv_short_rows_seq<T, B><<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, \
+                                                                            op->nloc, chunk)
+        if (chunk > 0 && seq == 2)
+            PYCI_SEQ(2, 8);
+        else if (chunk > 0 && seq == 1)
+            PYCI_SEQ(1, 8);
+        else if (chunk > 0 && seq == 3)
+            PYCI_SEQ(3, 8);
+        else if (chunk > 0 && seq == 4)
+            PYCI_SEQ(4, 6);
+        else if (chunk > 0 && seq == 6)
+            PYCI_SEQ(6, 5);
         else
             spmv_short_rows<<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, op->nloc,
                                                                       chunk);
+#undef PYCI_SEQ
         ctx->launches++;
         PYCI_CUDA(cudaGetLastError());
         return PYCI_OK;
