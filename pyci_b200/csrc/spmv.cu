@@ -513,10 +513,13 @@ int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev) {
             chunk = (chunk_env + 7) & ~7L;
             gg = (op->nloc + chunk - 1) / chunk;
         }
-        // the entry-per-lane kernel (contiguous ranges only); PYCI_B200_SPMV_SEQ=0: the pair-per-lane kernel.  5 M
-        // determinants: 2.013 ms -> 1.752 ms = 0.835 of the HBM peak; 1 / 2 / 3 trips in flight are within 1 %, 4 and 6
-        // spill and lose (1.92 / 2.12 ms)
-        static const int seq = getenv("PYCI_B200_SPMV_SEQ") ? atoi(getenv("PYCI_B200_SPMV_SEQ")) : 2;
+        // the entry-per-lane kernel (contiguous ranges only); PYCI_B200_SPMV_SEQ=0: the pair-per-lane kernel, k: k trips
+        // requested per loop iteration.  5 M determinants (x = 40 MB, L2-resident): 2.013 ms -> 1.76 / 1.76 / 1.74 ms at
+        // k = 1 / 2 / 3 = 0.83 of the HBM peak, 1.92 / 2.12 ms at 4 / 6.  One rank's shard of the 50 M-determinant
+        // operator (x = 400 MB, tools/spmv_shard.py): 3.96 ms -> 2.95 / 4.31 / 3.05 / 3.00 / 3.28 ms at k = 1 / 2 / 3 / 4 / 6
+        // (k = 2 is reproducibly the slow one there: the compiler's interleaving of its unrolled loop) -- one trip per
+        // iteration, which the compiler unrolls four times and pipelines itself, is the default.
+        static const int seq = getenv("PYCI_B200_SPMV_SEQ") ? atoi(getenv("PYCI_B200_SPMV_SEQ")) : 1;
 #define PYCI_SEQ(T, B)                                                                                              \
     spmv_short_rows_seq<T, B><<<(unsigned)gg, SPMV_BLOCK, 0, ctx->stream>>>(op->indptr, op->cols, op->vals, x_dev, y_dev, \
                                                                             op->nloc, chunk)
