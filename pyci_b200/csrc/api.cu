@@ -650,7 +650,9 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
         return PYCI_OK;
     }
     // output row pointer: the full row (general) or its col <= row prefix (symmetric, sparseop.cpp:223,262,431)
-    long *outptr = nullptr;
+    long *outptr = nullptr, *didx = nullptr;
+    double *dval = nullptr;
+    auto body = [&]() -> int { // (every early return below leaves through the frees after the lambda)
     PYCI_CUDA(dev_malloc(&outptr, sizeof(long) * (size_t)(nloc + 1)));
     if (op->symmetric) {
         PYCI_TRY(scan_counts(ctx, op->lowcnt, nloc, outptr, nullptr)); // multi-block scan of the prefix counts
@@ -664,8 +666,6 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
     if ((indices || data) && total > 0) {
         // widen to the reference's int64 indices on the device in bounded chunks of rows
         const long chunk_entries = 1L << 26; // 64 Mi entries -> 1 GiB of staging
-        long *didx = nullptr;
-        double *dval = nullptr;
         const long cap = std::min(total, chunk_entries + (long)INT32_MAX / 2);
         long r0 = 0;
         while (r0 < nloc && rc == PYCI_OK) {
@@ -694,11 +694,14 @@ int pyci_op_export_csr(pyci_op *op, long *indptr, long *indices, double *data) {
             }
             r0 = r1;
         }
-        dev_free(didx);
-        dev_free(dval);
     }
-    dev_free(outptr);
     return rc;
+    };
+    const int rc_all = body();
+    dev_free(didx);
+    dev_free(dval);
+    dev_free(outptr);
+    return rc_all;
 }
 
 int pyci_op_export_rows(pyci_op *op, long nrows, const long *rows, long cap, long *indptr, long *indices, double *data) {
@@ -833,21 +836,24 @@ int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, doubl
     double *x = nullptr, *y = nullptr;
     void *flush = nullptr;
     const long nx = std::max<long>(op->ncol, 1);
-    PYCI_CUDA(dev_malloc(&x, sizeof(double) * nx));
-    PYCI_CUDA(dev_malloc(&y, sizeof(double) * std::max<long>(op->nloc, 1)));
-    if (flush_bytes > 0)
-        PYCI_CUDA(dev_malloc(&flush, (size_t)flush_bytes));
     std::vector<double> hx((size_t)nx);
-    u64 sdd = 0x9e3779b97f4a7c15ULL;
-    for (long i = 0; i < nx; ++i) {
-        sdd ^= sdd << 13; sdd ^= sdd >> 7; sdd ^= sdd << 17;
-        hx[i] = (double)(sdd >> 11) * (1.0 / 9007199254740992.0) - 0.5;
-    }
-    PYCI_CUDA(cudaMemcpyAsync(x, hx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
-    std::vector<cudaEvent_t> ev(2 * (size_t)reps);
-    for (auto &e : ev)
-        PYCI_CUDA(cudaEventCreate(&e));
-    int rc = PYCI_OK;
+    std::vector<cudaEvent_t> ev(2 * (size_t)reps, nullptr);
+    auto setup = [&]() -> int { // (a failure here leaves through the clean-up at the end)
+        PYCI_CUDA(dev_malloc(&x, sizeof(double) * nx));
+        PYCI_CUDA(dev_malloc(&y, sizeof(double) * std::max<long>(op->nloc, 1)));
+        if (flush_bytes > 0)
+            PYCI_CUDA(dev_malloc(&flush, (size_t)flush_bytes));
+        u64 sdd = 0x9e3779b97f4a7c15ULL;
+        for (long i = 0; i < nx; ++i) {
+            sdd ^= sdd << 13; sdd ^= sdd >> 7; sdd ^= sdd << 17;
+            hx[i] = (double)(sdd >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+        }
+        PYCI_CUDA(cudaMemcpyAsync(x, hx.data(), sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+        for (auto &e : ev)
+            PYCI_CUDA(cudaEventCreate(&e));
+        return PYCI_OK;
+    };
+    int rc = setup();
     for (int it = -warmup; it < reps && rc == PYCI_OK; ++it) {
         if (flush)
             cudaMemsetAsync(flush, it & 0xff, (size_t)flush_bytes, st);
@@ -866,8 +872,11 @@ int pyci_op_time_spmv(pyci_op *op, int warmup, int reps, long flush_bytes, doubl
         cudaEventElapsedTime(&t, ev[2 * it], ev[2 * it + 1]);
         ms[it] = t;
     }
+    if (rc != PYCI_OK)
+        cudaStreamSynchronize(st); // hx is read by the upload
     for (auto &e : ev)
-        cudaEventDestroy(e);
+        if (e)
+            cudaEventDestroy(e);
     dev_free(x);
     dev_free(y);
     dev_free(flush);

@@ -479,9 +479,16 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     PYCI_CUDA(dev_malloc(&S.dring, sizeof(double) * S.small_cap * Solver::RING));
     PYCI_CUDA(cudaEventCreate(&S.e0));
     PYCI_CUDA(cudaEventCreate(&S.e1));
-    cudaEvent_t t_begin, t_end;
-    PYCI_CUDA(cudaEventCreate(&t_begin));
-    PYCI_CUDA(cudaEventCreate(&t_end));
+    struct EventGuard { // destroyed on every return path
+        cudaEvent_t e = nullptr;
+        ~EventGuard() {
+            if (e)
+                cudaEventDestroy(e);
+        }
+    } guard_begin, guard_end;
+    PYCI_CUDA(cudaEventCreate(&guard_begin.e));
+    PYCI_CUDA(cudaEventCreate(&guard_end.e));
+    const cudaEvent_t t_begin = guard_begin.e, t_end = guard_end.e;
     PYCI_CUDA(cudaEventRecord(t_begin, S.st));
 
     // ---- start vectors
@@ -671,8 +678,6 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     PYCI_CUDA(cudaStreamSynchronize(S.st));
     float total_ms = 0;
     cudaEventElapsedTime(&total_ms, t_begin, t_end);
-    cudaEventDestroy(t_begin);
-    cudaEventDestroy(t_end);
     S.stats.seconds = total_ms * 1e-3;
     S.stats.spmv_seconds = spmv_ms * 1e-3;
     if (stats_out)
