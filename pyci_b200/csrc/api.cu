@@ -616,6 +616,8 @@ void pyci_op_destroy(pyci_op *op) {
     dev_free(op->xbuf);
     dev_free(op->ybuf);
     dev_free(op->spmv_part);
+    dev_free(op->gather_stage);
+    dev_free(op->bounds_dev);
     delete op;
 }
 

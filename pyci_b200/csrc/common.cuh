@@ -145,6 +145,9 @@ struct pyci_op {
     int spmv_part_n = 0;
     // scratch for host-facing matvec
     double *xbuf = nullptr, *ybuf = nullptr;
+    // nnz-balanced partition: staging of the all-gather of unequal shards [nranks][npad], the partition on the device
+    double *gather_stage = nullptr;
+    long *bounds_dev = nullptr;
 };
 
 // Makes ctx's device current and its stream the target of dev_malloc / dev_free on this thread.
@@ -189,7 +192,7 @@ int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci
 // rebalance.cu: moves rows between neighbouring ranks so that every rank stores the same number of entries (collective)
 int op_rebalance(pyci_ctx *ctx, pyci_op *op);
 // every rank's shard of a row-distributed vector, concatenated in row order, on every rank
-int op_allgather_rows(pyci_ctx *ctx, const pyci_op *op, const double *send_dev, double *recv_dev);
+int op_allgather_rows(pyci_ctx *ctx, pyci_op *op, const double *send_dev, double *recv_dev);
 // spmv.cu
 int spmv_launch(pyci_op *op, const double *x_dev, double *y_dev);
 // solver.cu
