@@ -141,7 +141,10 @@ PYCI_API double pyci_wfn_ext_seconds(const pyci_wfn *wfn);
 /* SparseOp::SparseOp + update (sparseop.cpp:49-71,186-201): rows [0,nrow) x columns [0,ncol) of H
  * in the determinant basis of wfn; nrow/ncol < 0 mean ndet.  symmetric != 0 gives the operator the
  * reference's lower-triangular export; on the device the full rows are kept for a gather SpMV.
- * With a communicator, rank r owns the contiguous row block r of ceil(nrow/nranks) rows. */
+ * With a communicator, rank r builds the contiguous row block r of ceil(nrow/nranks) rows.  The rows of a selected
+ * space are then re-partitioned (collectively) so that every rank stores the same number of entries -- contiguous
+ * ranges balanced by nnz; pyci_op_row_begin / pyci_op_row_count report what the rank holds (PYCI_B200_NO_REBALANCE=1
+ * keeps the uniform blocks; complete spaces are uniform by construction). */
 PYCI_API int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
                   int symmetric, pyci_op **out);
 /* The row block that rank `rank` of `nranks` owns, built WITHOUT a communicator: construction has no collective
@@ -151,12 +154,14 @@ PYCI_API int pyci_op_build(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *w
 PYCI_API int pyci_op_build_shard(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, long nrow, long ncol,
                         int symmetric, int rank, int nranks, pyci_op **out);
 PYCI_API void pyci_op_destroy(pyci_op *op);
-/* SparseOp::update (sparseop.cpp:175-201): grow a square symmetric operator built for the first op.nrow
- * determinants of wfn to all wfn.ndet of them (the caller appended determinants, e.g. with pyci_wfn_add_hci; the
- * first op.nrow determinants must be the ones the operator was built from, as for the reference).  Only the new
- * determinants are enumerated: their rows are built, and their entries with an old column are transposed into
- * the ends of the old rows (the device keeps full rows).  The exported CSR equals that of a fresh build.
- * PYCI_ERR_UNSUPPORTED for non-symmetric / rectangular operators and when row-sharded: rebuild instead. */
+/* SparseOp::update (sparseop.cpp:175-201): grow an operator built for the first op.nrow determinants of wfn to all
+ * wfn.ndet of them (the caller appended determinants, e.g. with pyci_wfn_add_hci; the first op.nrow determinants
+ * must be the ones the operator was built from, as for the reference).  Only the new determinants are enumerated.
+ * Symmetric (square): their rows are built, and their entries with an old column are transposed into the ends of
+ * the old rows (the device keeps full rows); the exported CSR equals that of a fresh build.  Non-symmetric: the new
+ * rows [op.nrow, ndet) x [0, ndet) are appended and the rows the operator has keep the columns they were built with,
+ * exactly what the reference's update leaves (NOT the fresh-build matrix).
+ * PYCI_ERR_UNSUPPORTED for symmetric operators with nrow != ncol and when row-sharded: rebuild instead. */
 PYCI_API int pyci_op_update(pyci_op *op, const pyci_ham *ham, const pyci_wfn *wfn);
 
 PYCI_API long pyci_op_nrow(const pyci_op *op);
