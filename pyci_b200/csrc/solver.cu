@@ -543,10 +543,6 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     if (const char *e = getenv("PYCI_B200_SOLVER_KEEP"))
         keep_target = std::max(nroot, std::min(mmax - nroot, atoi(e)));
     keep_target = std::min(keep_target, mmax - nroot);
-    // GD+k restarts (PYCI_B200_SOLVER_PLUSK=0 turns them off): Ritz coefficients of the previous step, per root
-    const bool plusk = !(getenv("PYCI_B200_SOLVER_PLUSK") && atoi(getenv("PYCI_B200_SOLVER_PLUSK")) == 0);
-    std::vector<double> prev_coef((size_t)nroot * mmax, 0.0), Gsave((size_t)mmax * mmax, 0.0);
-    int prev_m = 0;
     bool done = false;
     double spmv_ms = 0.0;
     long iter = 0;
@@ -575,7 +571,6 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
                 Gw[(size_t)i * m + j] = 0.5 * (G[(size_t)i * mmax + j] + G[(size_t)j * mmax + i]);
         jacobi_eigh(Gw, m, theta, Z);
         tr[1] += now() - tp;
-        // (the Ritz coefficients of the previous step stay in prev_coef until this step's restart decision is made)
         tp = now();
         // residuals and corrections
         const int nr = std::min(nroot, m);
@@ -619,60 +614,22 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
         int nunconv = 0;
         for (int r = 0; r < nr; ++r)
             nunconv += !conv[r];
-        bool restarted = false;
         if (m + nunconv > mmax) {
-            if (plusk)
-                for (int i = 0; i < m; ++i) // the projected matrix before it is overwritten (couplings of "+k" columns)
-                    for (int j = 0; j < m; ++j)
-                        Gsave[(size_t)i * mmax + j] = 0.5 * (G[(size_t)i * mmax + j] + G[(size_t)j * mmax + i]);
+            // (Measured and not kept: GD+k, i.e. also keeping the part of the previous step's Ritz vector that the kept
+            // ones do not span -- 497 against 503 products at the default subspace of the 5 M-determinant config-5-style
+            // operator, 492 / 527 at 8 vectors, 500 / 494 at 20: with half the basis kept the momentum direction is
+            // already in it.)
             // Thick restart: keep the lowest `keep` Ritz vectors (the wanted ones first), not only the wanted ones --
             // collapsing to the current approximation throws the Krylov information of the subspace away and costs
             // two to three times the matvecs on dense spectra (config 5).  V <- V Z, W <- W Z in place, G = diag(theta).
             int keep = std::max(nr, std::min(m - 1, keep_target));
             if (m > ROT_MAXM)
                 keep = nr;
-            int total = keep; // kept Ritz vectors + the "+k" directions below
-            std::vector<double> extra_diag;
             if (keep > nr) {
                 std::memcpy(S.hZ, Z.data(), sizeof(double) * (size_t)m * m);
-                // GD+k (Stathopoulos & Saad): next to the lowest Ritz vectors keep, for every wanted root, the part of
-                // the PREVIOUS step's Ritz vector that the kept ones do not span -- the direction a locally optimal CG
-                // would carry over; it is what lets a restarted small basis converge like an unrestarted one.  In
-                // coefficient space it is a column p orthogonal to the kept columns of Z, so the rotated basis stays
-                // orthonormal and the projected matrix diagonal: (p, Gp) on the new diagonal, zeros beside it.
-                if (plusk && prev_m > 0 && prev_m <= m) {
-                    for (int r = 0; r < nr && total < std::min(m, mmax - nroot); ++r) {
-                        std::vector<double> pv((size_t)m, 0.0);
-                        for (int i = 0; i < prev_m; ++i)
-                            pv[(size_t)i] = prev_coef[(size_t)r * mmax + i];
-                        for (int pass = 0; pass < 2; ++pass)
-                            for (int c = 0; c < total; ++c) {
-                                double d = 0.0;
-                                for (int i = 0; i < m; ++i)
-                                    d += S.hZ[(size_t)i * m + c] * pv[(size_t)i];
-                                for (int i = 0; i < m; ++i)
-                                    pv[(size_t)i] -= d * S.hZ[(size_t)i * m + c];
-                            }
-                        double nn = 0.0;
-                        for (int i = 0; i < m; ++i)
-                            nn += pv[(size_t)i] * pv[(size_t)i];
-                        if (!(nn > 1.0e-12))
-                            continue; // the previous Ritz vector lies in the span of the kept ones
-                        const double inv = 1.0 / std::sqrt(nn);
-                        for (int i = 0; i < m; ++i)
-                            S.hZ[(size_t)i * m + total] = pv[(size_t)i] * inv;
-                        double q = 0.0; // (p, G p) with the symmetrised projected matrix
-                        for (int i = 0; i < m; ++i)
-                            for (int j = 0; j < m; ++j)
-                                q += S.hZ[(size_t)i * m + total] * 0.5 * (G[(size_t)i * mmax + j] + G[(size_t)j * mmax + i]) *
-                                     S.hZ[(size_t)j * m + total];
-                        extra_diag.push_back(q);
-                        ++total;
-                    }
-                }
                 PYCI_CUDA(cudaMemcpyAsync(S.dZ, S.hZ, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, S.st));
-                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.V, S.ld, m, total, S.dZ, S.nloc);
-                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.W, S.ld, m, total, S.dZ, S.nloc);
+                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.V, S.ld, m, keep, S.dZ, S.nloc);
+                rotate_kernel<<<S.grid, RB, sizeof(double) * ((size_t)m * m + 2), S.st>>>(S.W, S.ld, m, keep, S.dZ, S.nloc);
                 ctx->launches += 2;
                 PYCI_CUDA(cudaStreamSynchronize(S.st)); // hZ is reused by the next restart
             } else {
@@ -682,34 +639,8 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
             std::fill(G.begin(), G.end(), 0.0);
             for (int r = 0; r < keep; ++r)
                 G[(size_t)r * mmax + r] = theta[r];
-            // the projected matrix is diagonal in the kept Ritz vectors; a "+k" column p is orthogonal to them but not
-            // an eigenvector: its couplings (Z_r, G p) = theta_r (Z_r, p) vanish, (p, G p') between two of them do not
-            for (int e = keep; e < total; ++e)
-                G[(size_t)e * mmax + e] = extra_diag[(size_t)(e - keep)];
-            if (total - keep > 1) {
-                for (int e = keep; e < total; ++e)
-                    for (int f = e + 1; f < total; ++f) {
-                        double q = 0.0;
-                        for (int i = 0; i < m; ++i)
-                            for (int j = 0; j < m; ++j)
-                                q += S.hZ[(size_t)i * m + e] * Gsave[(size_t)i * mmax + j] * S.hZ[(size_t)j * m + f];
-                        G[(size_t)e * mmax + f] = G[(size_t)f * mmax + e] = q;
-                    }
-            }
-            m = total;
-            // in the new basis the current Ritz vector of root r is the unit vector e_r
-            std::fill(prev_coef.begin(), prev_coef.end(), 0.0);
-            for (int r = 0; r < nr; ++r)
-                prev_coef[(size_t)r * mmax + r] = 1.0;
-            prev_m = m;
-            restarted = true;
+            m = keep;
             S.stats.restarts++;
-        }
-        if (!restarted) { // remember this step's Ritz coefficients for the "+k" of a later restart
-            for (int r = 0; r < nr; ++r)
-                for (int i = 0; i < m; ++i)
-                    prev_coef[(size_t)r * mmax + i] = Z[(size_t)i * m + r];
-            prev_m = m;
         }
         // expand
         nnew = 0;
