@@ -139,6 +139,10 @@ spmv_short_rows_seq(const long *__restrict__ indptr, const int *__restrict__ col
     }
 }
 
+// (ncu of the entry-per-lane kernel, profiles/r3o: 628 us against 723 us on 2 M determinants, DRAM 58 -> 66 %, the L1
+// data pipe 85 -> 93 % busy -- still the limit.  The reduction's shuffles go through the same pipe; reducing two rows
+// of a warp together, five shuffle steps per two rows, was measured and is slower, 1.83 against 1.75 ms: the second
+// row waits behind the first.)
 // Measured on the 5 M-determinant selected space (2.02 ms, 0.72 of the HBM peak; ncu: 81 % of the warp samples wait on
 // a long scoreboard, L1 hit rate of the gathers 59 %) and NOT kept -- none of them moves the number, the x gathers are
 // what the warps wait for: touching the warp's next row with prefetch.global.L2 (2.007 ms); three / four trips of a
