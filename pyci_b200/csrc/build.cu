@@ -34,6 +34,8 @@ __global__ void diag_kernel(BuildParams P) {
 
 constexpr int UNROLL = 4;
 constexpr int RANK_SORT_MAX = 320; // rows up to this many entries are ordered by a rank sort, longer ones by the radix sort
+constexpr int RANK_SORT_MIN = 48;  // ... and rows of more than this many by the bucketed form of it
+constexpr int SORT_BUCKETS = 512;  // buckets of the bucketed rank sort: a monotone map of [0, ncol) (two u32 arrays)
 
 // ---- count pass ---------------------------------------------------------------------------------
 // hitlist != nullptr: the hits of a row (candidate index, column) are also recorded, up to `cap` per row, so that
@@ -251,7 +253,8 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
     u32 *hist = gscratch ? reinterpret_cast<u32 *>(smem_raw) : reinterpret_cast<u32 *>(valbuf + P.maxrow);
     const int nbins = 1 << P.sort_dbits, nw = blockDim.x >> 5;
     u32 *tot = hist + nw * nbins;
-    unsigned char *tbase = reinterpret_cast<unsigned char *>(tot + nbins);
+    // (the counters double as the two arrays of the bucketed rank sort: sort_counter_words on the host side)
+    unsigned char *tbase = reinterpret_cast<unsigned char *>(hist + max((nw + 1) * nbins, 2 * SORT_BUCKETS));
     const RowTables T = carve_tables(tbase, nSa, nSb);
     uchar2 *pairs = reinterpret_cast<uchar2 *>(tbase + tables_bytes(nSa, nSb));
     __shared__ RowShared rs;
@@ -352,7 +355,62 @@ __global__ void __launch_bounds__(256) fill_kernel(BuildParams P, DetIndex<KM> i
         __syncthreads();
         const int m = rs.count;
         const u64 *sorted;
-        if (m <= RANK_SORT_MAX) {
+        if (m > RANK_SORT_MIN && m <= RANK_SORT_MAX) {
+            // Bucketed rank sort.  ncu of the plain rank sort below on a config-5-style space (profiles/r3q): two thirds
+            // of the kernel's instructions, m / 2 shared-memory loads and m compares for every entry.  A column maps
+            // monotonically to one of 512 buckets of [0, ncol); counts, one scan and a scatter group the row by bucket
+            // (in bucket order = column order), and an entry is then ranked only against the few entries of its own
+            // bucket -- the connected determinants of a selected space are spread over the whole list, runs of
+            // neighbouring columns are a handful long.  A row whose entries all fall into one bucket costs what the
+            // plain rank sort costs, never more (m <= 320).
+            u32 *cnt = hist, *bstart = hist + SORT_BUCKETS;
+            const u64 mul = ((u64)SORT_BUCKETS << 32) / (u64)max(P.ncol, 1L); // bucket = col * mul >> 32 < SORT_BUCKETS
+            for (int b = threadIdx.x; b < SORT_BUCKETS; b += blockDim.x)
+                cnt[b] = 0u;
+            __syncthreads();
+            for (int e = threadIdx.x; e < m; e += blockDim.x)
+                atomicAdd(&cnt[(u32)(((keyA[e] >> 32) * mul) >> 32)], 1u);
+            __syncthreads();
+            if (threadIdx.x < 32) { // exclusive scan of the counts: sixteen consecutive buckets per lane
+                constexpr int PER = SORT_BUCKETS / 32;
+                u32 loc = 0u;
+#pragma unroll
+                for (int q = 0; q < PER; ++q)
+                    loc += cnt[lane * PER + q];
+                u32 run = loc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 up = __shfl_up_sync(0xffffffffu, run, o);
+                    if (lane >= o)
+                        run += up;
+                }
+                run -= loc;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const u32 c = cnt[lane * PER + q];
+                    bstart[lane * PER + q] = run;
+                    cnt[lane * PER + q] = run; // cursor of the scatter; ends up at the bucket's end
+                    run += c;
+                }
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < m; e += blockDim.x) {
+                const u64 key = keyA[e];
+                keyB[atomicAdd(&cnt[(u32)(((key >> 32) * mul) >> 32)], 1u)] = key;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < m; e += blockDim.x) {
+                const u64 key = keyB[e];
+                const u32 col = (u32)(key >> 32), b = (u32)(((u64)col * mul) >> 32);
+                const u32 s = bstart[b], t = cnt[b];
+                u32 rank = s;
+                for (u32 f = s; f < t; ++f)
+                    rank += (u32)(keyB[f] >> 32) < col;
+                keyA[rank] = key;
+            }
+            __syncthreads();
+            sorted = keyA;
+        } else if (m <= RANK_SORT_MAX) {
             // short row (the rows of a selected space hold ~10^2 entries): rank sort -- entry e goes to the number of
             // entries with a smaller key; every thread reads the same key at a time (shared-memory broadcast).  The
             // radix sort below costs ~10^4 warp instructions per row whatever its length (ncu r2d).
@@ -1010,9 +1068,10 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             if (joined) // no row is enumerated by the fill pass: the threads of a CTA only share the row's hits
                 block = pick_block(2 * std::max<long>(1, nnz / std::max<long>(nloc, 1)));
             // keys (ping-pong) + values + radix counters + tables + pair table
+            size_t tab_used = tab_bytes; // excitation tables in shared memory (dropped below when no row is enumerated)
             auto smem_for = [&](int blk, long rows) {
-                return (size_t)24 * (size_t)rows + sizeof(u32) * ((size_t)(blk / 32) + 1) * (1u << P.sort_dbits) + tab_bytes +
-                       pair_bytes;
+                const size_t counters = std::max<size_t>(((size_t)(blk / 32) + 1) * (1u << P.sort_dbits), 2 * SORT_BUCKETS);
+                return (size_t)24 * (size_t)rows + sizeof(u32) * counters + tab_used + pair_bytes;
             };
             const int full_rows = P.maxrow;
             while (block > 32 && (long)smem_for(block, full_rows) > (long)ctx->smem_optin)
@@ -1024,14 +1083,15 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                                    (forced_cap > 0 && forced_cap < full_rows);
             if (long_rows) {
                 // a few rows are too long for shared memory: those go through HBM in a second launch
-                block = pick_block((long)P.ncand / 4);
+                if (!joined) // (rows from recorded hits keep the block chosen for their mean length)
+                    block = pick_block((long)P.ncand / 4);
                 const long fit = ((long)ctx->smem_optin - (long)smem_for(block, 0) - 1024) / 24;
                 if (fit < 64)
                     PYCI_FAIL(PYCI_ERR_UNSUPPORTED, "excitation tables (%zu bytes) leave no room for a row buffer",
                               smem_for(block, 0));
                 short_cap = (int)(std::min<long>(fit, forced_cap > 0 ? forced_cap : 4096) & ~1L);
             }
-            const size_t smem = smem_for(block, short_cap);
+            size_t smem = smem_for(block, short_cap);
             // most candidates miss (selected space): evaluate elements for hits only
             const bool lazy = !analytic && (double)nnz < 0.25 * (double)nloc * ((double)P.ncand + 1.0);
             // rows with more hits than the recorded list holds: a second join pass stages their hits in the CSR arrays
@@ -1048,6 +1108,15 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                     staged = used;
                 }
             }
+            // Every row comes from recorded or staged hits: the fill pass enumerates nothing, so the single-excitation
+            // tables (14 KB of the 28 KB per CTA at 64 spin-orbitals / 20 electrons) stay out of shared memory and
+            // twice as many rows are in flight per SM.
+            u32 nSa_k = nSa, nSb_k = nSb;
+            if (joined && (maxrow - 1 <= hitcap || staged) && !getenv("PYCI_B200_FILL_KEEP_TABLES")) {
+                tab_used = 0;
+                nSa_k = nSb_k = 0;
+                smem = smem_for(block, short_cap);
+            }
             PYCI_CUDA(cudaEventRecord(ctx->ev[4], st));
             fill_timed = true;
             auto launch = [&](auto kern) -> int {
@@ -1057,14 +1126,14 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
                 PYCI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
                 const long grid = std::min<long>(nloc, (long)ctx->sm_count * std::max(per_sm, 1));
-                kern<<<(unsigned)grid, block, smem, st>>>(Ps, ix, nSa, nSb, hitlist, hitcap, nullptr, short_cap, staged);
+                kern<<<(unsigned)grid, block, smem, st>>>(Ps, ix, nSa_k, nSb_k, hitlist, hitcap, nullptr, short_cap, staged);
                 ctx->launches++;
                 if (long_rows) {
                     const size_t smem2 = smem_for(block, 0);
                     PYCI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem2));
                     const long grid2 = std::min<long>(nloc, (long)ctx->sm_count * std::min(std::max(per_sm, 1), 2));
                     PYCI_CUDA(dev_malloc(&long_scratch, sizeof(u64) * 3 * (size_t)full_rows * (size_t)grid2));
-                    kern<<<(unsigned)grid2, block, smem2, st>>>(P, ix, nSa, nSb, hitlist, hitcap, long_scratch, short_cap,
+                    kern<<<(unsigned)grid2, block, smem2, st>>>(P, ix, nSa_k, nSb_k, hitlist, hitcap, long_scratch, short_cap,
                                                                 staged);
                     ctx->launches++;
                 }
