@@ -1112,7 +1112,9 @@ int run_build(pyci_ctx *ctx, const pyci_wfn *wfn, pyci_op *op, BuildParams &P, i
             // tables (14 KB of the 28 KB per CTA at 64 spin-orbitals / 20 electrons) stay out of shared memory and
             // twice as many rows are in flight per SM.
             u32 nSa_k = nSa, nSb_k = nSb;
-            if (joined && (maxrow - 1 <= hitcap || staged) && !getenv("PYCI_B200_FILL_KEEP_TABLES")) {
+            // (maxrow counts the diagonal where a row has one; rows beyond ncol of a rectangular operator do not, hence
+            // the comparison without the "- 1" of the staging test above: conservative by one entry)
+            if (joined && (maxrow <= hitcap || staged) && !getenv("PYCI_B200_FILL_KEEP_TABLES")) {
                 tab_used = 0;
                 nSa_k = nSb_k = 0;
                 smem = smem_for(block, short_cap);
