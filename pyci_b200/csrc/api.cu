@@ -893,24 +893,28 @@ int pyci_op_get_element(pyci_op *op, long i, long j, double *out) {
     if (i < op->row0 || i >= op->row0 + op->nloc)
         PYCI_FAIL(PYCI_ERR_VALUE, "row %ld is not held by this rank", i);
     *out = 0.0;
-    long ptr[2];
-    PYCI_CUDA(cudaMemcpyAsync(ptr, op->indptr + (i - op->row0), sizeof(long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
-    const long m = ptr[1] - ptr[0];
-    if (m <= 0)
-        return PYCI_OK;
-    std::vector<int> cols((size_t)m);
-    PYCI_CUDA(cudaMemcpyAsync(cols.data(), op->cols + ptr[0], sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
     // symmetric storage of the reference only holds j <= i (sparseop.cpp:89-94 searches the stored row)
     if (op->symmetric && j > i)
         return PYCI_OK;
-    auto it = std::lower_bound(cols.begin(), cols.end(), (int)std::min<long>(j, INT32_MAX));
-    if (it != cols.end() && *it == j) {
-        PYCI_CUDA(cudaMemcpyAsync(out, op->vals + ptr[0] + (it - cols.begin()), sizeof(double), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
+    if (op->ge_row != i) { // one trip to the device per row, not per element
+        op->ge_row = -1;
+        long ptr[2];
+        PYCI_CUDA(cudaMemcpyAsync(ptr, op->indptr + (i - op->row0), sizeof(long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
         PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+        const long m = std::max<long>(ptr[1] - ptr[0], 0);
+        op->ge_cols.resize((size_t)m);
+        op->ge_vals.resize((size_t)m);
+        if (m > 0) {
+            PYCI_CUDA(cudaMemcpyAsync(op->ge_cols.data(), op->cols + ptr[0], sizeof(int) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            PYCI_CUDA(cudaMemcpyAsync(op->ge_vals.data(), op->vals + ptr[0], sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            PYCI_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        op->ge_row = i;
     }
+    const std::vector<int> &cols = op->ge_cols;
+    auto it = std::lower_bound(cols.begin(), cols.end(), (int)std::min<long>(j, INT32_MAX));
+    if (it != cols.end() && *it == j)
+        *out = op->ge_vals[(size_t)(it - cols.begin())];
     return PYCI_OK;
 }
 

@@ -145,6 +145,11 @@ struct pyci_op {
     int spmv_part_n = 0;
     // scratch for host-facing matvec
     double *xbuf = nullptr, *ybuf = nullptr;
+    // pyci_op_get_element: host copy of the row asked for last (callers walk a row element by element,
+    // pyci/test/test_routines.py:75-78); -1 = none.  Every site that replaces cols/vals resets it.
+    long ge_row = -1;
+    std::vector<int> ge_cols;
+    std::vector<double> ge_vals;
     // nnz-balanced partition: staging of the all-gather of unequal shards [nranks][npad], the partition on the device
     double *gather_stage = nullptr;
     long *bounds_dev = nullptr;

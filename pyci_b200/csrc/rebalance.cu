@@ -247,6 +247,7 @@ int op_rebalance(pyci_ctx *ctx, pyci_op *op) {
         dev_free(op->spmv_part);
         op->indptr = nip;
         op->cols = ncols;
+        op->ge_row = -1;
         op->vals = nvals;
         op->lowcnt = nlow;
         op->diag = ndiag;

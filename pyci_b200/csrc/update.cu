@@ -184,6 +184,7 @@ int op_append_rows_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn,
         dev_free(op->spmv_part);
         op->indptr = nip;
         op->cols = ncols;
+        op->ge_row = -1;
         op->vals = nvals;
         op->lowcnt = nlow;
         op->diag = ndiag;
@@ -335,6 +336,7 @@ int op_update_impl(pyci_ctx *ctx, const pyci_ham *ham, const pyci_wfn *wfn, pyci
         dev_free(op->spmv_part);
         op->indptr = nip;
         op->cols = ncols;
+        op->ge_row = -1;
         op->vals = nvals;
         op->lowcnt = nlow;
         op->diag = ndiag;

@@ -1,0 +1,47 @@
+"""The reference's own test files, run UNCHANGED against this package (`import pyci` bound to pyci_b200 by
+tests/reference_suite_runner.py).  The files are not part of this repository: `make -C oracle ref` copies
+/root/reference/pyci/test as it lies into oracle/_ref/reftests/ (git-ignored, travels to the GPU box like the compiled
+reference beside it); without that copy the tests skip.
+
+Deselected, because the reference snapshot itself lacks the data file: the `he_ccpvqz` cases (no such FCIDUMP; the
+compiled reference fails on them with the same RuntimeError) and the li2 / h2o cases of test_compute_rdms and
+test_compute_transition_rdms (`<name>_spinres.npz` exists for be_ccpvdz only; everything those cases assert before the
+np.load passes, profiles/r4a_reference_suite.log).  Skipped by the suite's own conftest: the `bigmem` 3-/4-RDM test (out
+of scope).  test_odometer.py needs the pure-Python selectors of pyci/utility.py (out of scope)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUITE = os.path.join(ROOT, "oracle", "_ref", "reftests", "pyci_test")
+needs_suite = pytest.mark.skipif(not os.path.exists(os.path.join(SUITE, "test_routines.py")),
+                                 reason="oracle/_ref/reftests not built (needs /root/reference at build time)")
+
+
+def run_suite(*args):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "reference_suite_runner.py"), SUITE, *args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
+    assert r.returncode == 0, tail
+    return r.stdout
+
+
+@needs_suite
+def test_reference_wavefunction_and_hamiltonian_tests_pass_unchanged():
+    """pyci/test/test_wavefunction.py (constructors, bad occupations, file and array round trips, index/rank, excited
+    determinants, 65- and 129-orbital strings) and pyci/test/test_hamiltonian.py (FCIDUMP round trip): host side only."""
+    out = run_suite("test_wavefunction.py", "test_hamiltonian.py", "-k", "not he_ccpvqz")
+    assert " passed" in out and "failed" not in out
+
+
+@needs_suite
+@pytest.mark.gpu
+def test_reference_routines_tests_pass_unchanged():
+    """pyci/test/test_routines.py: test_solve_sparse (pinned energies), test_sparse_rectangular, test_compute_rdms,
+    test_compute_transition_rdms, test_run_hci, test_enpt2 and the hand-derived RDM elements — the hot path through the
+    reference's own assertions."""
+    absent = "he_ccpvqz or ((compute_rdms or transition_rdms) and (li2_ccpvdz or h2o_ccpvdz))"
+    out = run_suite("test_routines.py", "--durations=5", "-k", "not (%s)" % absent)
+    assert " passed" in out and "failed" not in out
