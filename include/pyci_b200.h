@@ -217,7 +217,9 @@ PYCI_API int pyci_op_set_spmv_shape(pyci_op *op, int threads_per_row, int ctas_p
  * streamed in lockstep by one CTA and share their gathers of x in L1; depth (2..4) = trips of (value, column)
  * loads every thread keeps in flight.  Tuning knobs only. */
 PYCI_API int pyci_op_set_spmv_block(pyci_op *op, int block_threads, int depth);
-/* SparseOp::get_element (sparseop.cpp:89-94); i must be a row of this rank */
+/* SparseOp::get_element (sparseop.cpp:89-94); i must be a row of this rank.  The row asked for last is kept on the
+ * host, so a walk along a row costs one device round trip (not thread-safe on one handle, like the reference's GIL-held
+ * call) */
 PYCI_API int pyci_op_get_element(pyci_op *op, long i, long j, double *out);
 
 typedef struct pyci_solve_stats {
