@@ -4,7 +4,17 @@ transforms, spin-block -> spin-orbital RDM conversion, excitation-level determin
 They only call the public ``_pyci`` surface."""
 import numpy as np
 
-__all__ = ["make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations"]
+__all__ = ["make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations",
+           "odometer_one_spin", "odometer_two_spin"]
+
+
+def __getattr__(name):
+    # pyci/utility.py:424-505 keeps the odometers in this namespace (`from pyci.utility import odometer_one_spin`,
+    # pyci/test/test_odometer.py:21); they live in pyci_b200/selectors.py, which imports the extension module
+    if name in ("odometer_one_spin", "odometer_two_spin"):
+        from pyci_b200 import selectors
+        return getattr(selectors, name)
+    raise AttributeError(name)
 
 
 def make_senzero_integrals(one_mo, two_mo):

@@ -158,3 +158,66 @@ def test_bulk_append_of_new_determinants():
         if nw > 1:  # a ragged array (not a whole number of determinants) is refused
             with pytest.raises(ValueError):
                 cls(*args)._append_new_dets(np.zeros(2 * nw + 1, dtype=np.uint64))
+
+
+def _selector_cases():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_selectors", os.path.join(os.path.dirname(__file__), "golden", "make_golden_selectors.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_selectors_match_the_reference_python_layer():
+    """add_seniorities / add_cost (odometers) / add_gkci against tests/golden/selectors.npz: determinant arrays made by the
+    reference's own Python functions over its compiled classes, insertion order included."""
+    import os
+    G = _selector_cases()
+    with np.load(os.path.join(os.path.dirname(__file__), "golden", "selectors.npz")) as f:
+        gold = {k: f[k] for k in f.files}
+
+    def same(w, tag):
+        return len(w) == len(gold[tag]) and (len(w) == 0 or np.array_equal(w.to_det_array(), gold[tag]))
+
+    for tag, shape, sens in G.SENIORITY:
+        w = pyci.fullci_wfn(*shape)
+        pyci.add_seniorities(w, *sens)
+        assert same(w, tag), tag
+    for tag, cls, shape, t, qmax in G.ODOMETER:
+        w = getattr(pyci, cls)(*shape)
+        pyci.add_cost(w, G.costs(shape[0], 7), qmax, t)
+        assert same(w, tag), tag
+        w2 = getattr(pyci, cls)(*shape)
+        odo = pyci.odometer_two_spin if cls == "fullci_wfn" else pyci.utility.odometer_one_spin
+        odo(w2, G.costs(shape[0], 7), t, qmax)
+        assert same(w2, tag), tag
+    for tag, cls, shape, kw in G.GKCI:
+        w = getattr(pyci, cls)(*shape)
+        kw = dict(kw)
+        if kw.get("mode") == "interval":
+            kw["energies"] = G.costs(shape[0] + 1, 11)
+        if kw.get("mode") == "nodes":
+            kw["mode"] = G.costs(shape[0] + 1, 13)
+        pyci.add_gkci(w, **kw)
+        assert same(w, tag), tag
+
+
+def test_selector_argument_errors():
+    """seniority_ci.py:43-52, gkci.py:63-67: wrong wave-function type -> TypeError, impossible seniority or unknown node
+    model -> ValueError."""
+    with pytest.raises(TypeError):
+        pyci.add_seniorities(pyci.doci_wfn(6, 2, 2), 0)
+    w = pyci.fullci_wfn(6, 3, 1)
+    for bad in (0, 3, 6):          # below nocc_up - nocc_dn, wrong parity, above the bound
+        with pytest.raises(ValueError):
+            pyci.add_seniorities(w, bad)
+    assert len(w) == 0
+    with pytest.raises(ValueError):
+        pyci.add_gkci(pyci.doci_wfn(6, 2, 2), mode="nope")
+    # seniority sectors partition the full space
+    full = pyci.fullci_wfn(6, 3, 1)
+    full.add_all_dets()
+    pyci.add_seniorities(w, 2, 4)
+    assert len(w) == len(full)

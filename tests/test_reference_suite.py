@@ -7,7 +7,7 @@ Deselected, because the reference snapshot itself lacks the data file: the `he_c
 compiled reference fails on them with the same RuntimeError) and the li2 / h2o cases of test_compute_rdms and
 test_compute_transition_rdms (`<name>_spinres.npz` exists for be_ccpvdz only; everything those cases assert before the
 np.load passes, profiles/r4a_reference_suite.log).  Skipped by the suite's own conftest: the `bigmem` 3-/4-RDM test (out
-of scope).  test_odometer.py needs the pure-Python selectors of pyci/utility.py (out of scope)."""
+of scope)."""
 import os
 import subprocess
 import sys
@@ -41,7 +41,8 @@ def test_reference_wavefunction_and_hamiltonian_tests_pass_unchanged():
 def test_reference_routines_tests_pass_unchanged():
     """pyci/test/test_routines.py: test_solve_sparse (pinned energies), test_sparse_rectangular, test_compute_rdms,
     test_compute_transition_rdms, test_run_hci, test_enpt2 and the hand-derived RDM elements — the hot path through the
-    reference's own assertions."""
+    reference's own assertions; pyci/test/test_odometer.py: all but one eigenvalue of three small operators as the
+    costs of an odometer selection."""
     absent = "he_ccpvqz or ((compute_rdms or transition_rdms) and (li2_ccpvdz or h2o_ccpvdz))"
-    out = run_suite("test_routines.py", "--durations=5", "-k", "not (%s)" % absent)
+    out = run_suite("test_routines.py", "test_odometer.py", "--durations=5", "-k", "not (%s)" % absent)
     assert " passed" in out and "failed" not in out
