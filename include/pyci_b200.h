@@ -232,7 +232,8 @@ typedef struct pyci_solve_stats {
 } pyci_solve_stats;
 
 /* SparseOp::solve_ci (sparseop.cpp:114-146): n lowest eigenpairs, evals[n] (ecore added),
- * evecs[n][nrow] row-major.  c0: nrow doubles or NULL; ncv: subspace size or -1 for
+ * evecs[n][nrow] row-major, in the reference's order for n > 1: largest of the n first (Spectra's default
+ * `sorting` of the selected pairs, sparseop.cpp:134; pyci/test/test_odometer.py depends on it).  c0: nrow doubles or NULL; ncv: subspace size or -1 for
  * min(nrow, max(2n+1, 20)); maxiter: -1 for 10*n*nrow; tol: residual tolerance relative to
  * max(eps^(2/3), |theta|) as in Spectra.  Errors follow sparseop.cpp:116-124,136.
  * Collective when row-sharded (NCCL all-gather of the trial vector every iteration). */

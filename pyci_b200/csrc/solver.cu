@@ -689,16 +689,20 @@ int solve_impl(pyci_op *op, long n, const double *c0, long ncv, long maxiter, do
     if (!done)
         PYCI_FAIL(PYCI_ERR_RUNTIME, "did not converge");
 
-    // results: evals (+ecore, sparseop.cpp:140-141), evecs[n][nrow] row-major (:142-144)
+    // results: evals (+ecore, sparseop.cpp:140-141), evecs[n][nrow] row-major (:142-144).  Order of the n lowest pairs:
+    // the reference calls Spectra's compute(SmallestAlge, maxit, tol) with the default `sorting` argument
+    // (sparseop.cpp:134), LargestAlge - the n smallest eigenvalues come back LARGEST FIRST.  The reference's
+    // pyci/test/test_odometer.py:38-40,47-60 depends on it (costs = -evals of the len-1 lowest roots).
     for (int r = 0; r < nroot; ++r)
-        evals[r] = theta[r] + op->ecore;
+        evals[nroot - 1 - r] = theta[r] + op->ecore;
     for (int r = 0; r < nroot; ++r) {
         const double *src = S.X + (size_t)r * S.ld;
         if (R > 1) {
             PYCI_TRY(op_allgather_rows(ctx, op, src, S.xfull));
             src = S.xfull;
         }
-        PYCI_CUDA(cudaMemcpyAsync(evecs + (size_t)r * nrow, src, sizeof(double) * nrow, cudaMemcpyDeviceToHost, S.st));
+        PYCI_CUDA(cudaMemcpyAsync(evecs + (size_t)(nroot - 1 - r) * nrow, src, sizeof(double) * nrow, cudaMemcpyDeviceToHost,
+                                  S.st));
     }
     PYCI_CUDA(cudaStreamSynchronize(S.st));
     return PYCI_OK;

@@ -94,8 +94,8 @@ x3 = seeded_vec(len(sel), 8)
 y3, y3o = op3(x3), O.matvec(ip2, ix2, dv2, x3, True)
 assert np.max(np.abs(y3 - y3o)) <= 1e-11 * np.max(np.abs(y3o))
 e3, c3 = op3.solve(n=2, tol=1e-9)
-assert abs(e3[0] - e2o) < 1e-9 and c3.shape == (2, len(sel)), (e3, e2o)
-r3 = op3(c3[0]) - (e3[0] - 0.0) * c3[0]
+assert abs(e3[-1] - e2o) < 1e-9 and e3[0] > e3[-1] and c3.shape == (2, len(sel)), (e3, e2o)  # largest of the n lowest first
+r3 = op3(c3[-1]) - (e3[-1] - 0.0) * c3[-1]
 assert np.linalg.norm(r3) < 1e-6
 if rank == 0:
     print("rebalance: worst rank %d -> %d stored entries of %d" % (uniform_worst, balanced_worst, sum(p[3] for p in parts)), flush=True)

@@ -290,7 +290,7 @@ def test_solve_guards_and_edge_cases(pyci):
     es, cs = op.solve(n=len(wfn) - 1, tol=1e-10)     # several roots (test_odometer.py style)
     ip, ix, dv = O.sparse_op(O.FULLCI, ham.nbasis, 1, 1, wfn.to_det_array(), (ham.one_mo, ham.two_mo))
     w = np.linalg.eigvalsh(O.full_symmetric(ip, ix, dv, len(wfn)).toarray()) + ham.ecore
-    np.testing.assert_allclose(np.sort(es), w[:len(es)], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(es, w[:len(es)][::-1], rtol=0, atol=1e-9)   # largest of the n lowest first
     # single determinant: E = H00 + ecore, c = [1]  (sparseop.cpp:120-124)
     one = pyci.fullci_wfn(ham.nbasis, 1, 1)
     one.add_hartreefock_det()
@@ -311,7 +311,11 @@ def test_solve_guards_and_edge_cases(pyci):
     e3, c3 = op.solve(n=3, tol=1e-9)
     ip, ix, dv = O.sparse_op(O.FULLCI, ham.nbasis, 2, 2, wfn.to_det_array(), (ham.one_mo, ham.two_mo))
     w = np.linalg.eigvalsh(O.full_symmetric(ip, ix, dv, len(wfn)).toarray()) + ham.ecore
-    np.testing.assert_allclose(e3, w[:3], rtol=0, atol=1e-9)
+    # the three lowest, largest first: Spectra's default sorting of the selected pairs (sparseop.cpp:134), which
+    # pyci/test/test_odometer.py relies on
+    np.testing.assert_allclose(e3, w[:3][::-1], rtol=0, atol=1e-9)
+    for k in range(3):  # every vector sits beside its own value
+        assert np.linalg.norm(op(c3[k]) - (e3[k] - ham.ecore) * c3[k]) < 1e-6
 
 
 def test_unsupported_and_invalid_inputs_fail_loudly(pyci):
