@@ -814,6 +814,9 @@ def run_b200(args, spec, rank, world, local):
         note("config 5")
         s5 = workload_spec("cfg5")
         s5["key"] = "cfg5"
+        # the headline line is complete at this point: a leg that hangs (a rank-local failure leaves the others inside a
+        # collective) must not lose it
+        guard = leg_watchdog(float(os.environ.get("PYCI_B200_LEG_TIMEOUT", "420")), rank, line, "cfg5", s5["label"])
         try:
             r5, l5 = measure_case(B, s5, 1, 1, gate_target=max(200, args.gate_rows // 4), rdm=True)
             l5["dwfn"].close()
@@ -823,6 +826,7 @@ def run_b200(args, spec, rank, world, local):
                                                 "build", "time_to_e0", "rdm")}
         except Exception as exc:  # the headline line must survive a failure of this extra leg; it is reported, not hidden
             line["cfg5"] = {"workload": s5["label"], "error": "%s: %s" % (type(exc).__name__, exc)}
+        guard.cancel()
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         note("CPU baseline (reference, host cores)")
         line["cpu_baseline"] = cpu_sample(spec, args.cpu_seconds)
@@ -969,6 +973,24 @@ def emit(line):
     out = _JSON_OUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def leg_watchdog(seconds, rank, line, key, label):
+    """Timer around an extra leg that runs after the headline numbers are in `line`: if the leg has not finished after
+    `seconds`, rank 0 prints the line with the leg reported as timed out and every rank leaves the process (a hung
+    collective cannot be interrupted from Python).  Returns the timer; cancel() it when the leg is done."""
+    def fire():
+        if rank == 0:
+            line[key] = {"workload": label, "error": "watchdog: leg not finished after %.0f s; line printed without it" % seconds}
+            note("watchdog: %s leg abandoned" % key)
+            emit(line)
+        else:
+            time.sleep(5.0)  # rank 0 prints first
+        os._exit(0 if line.get("parity", {}).get("ok", False) else 1)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
 
 
 def dwfn_index_seconds(cabi, dwfn):

@@ -78,3 +78,20 @@ def test_golden_e0_lookup():
     spec = bench.workload_spec("cfg4")
     spec["key"] = "cfg4"
     assert bench.golden_e0(spec) == (None, None, None)
+
+
+def test_leg_watchdog_prints_the_line_when_an_extra_leg_hangs():
+    """bench.leg_watchdog: the headline line survives an extra leg that never returns; a cancelled timer does nothing."""
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "line = {'metric': 'm', 'parity': {'ok': True}}; "
+            "bench.leg_watchdog(0.3, int(sys.argv[1]), line, 'cfg5', 'label'); time.sleep(30)") % ROOT
+    out = subprocess.run([sys.executable, "-c", code, "0"], capture_output=True, text=True, timeout=25)
+    assert out.returncode == 0
+    d = json.loads(out.stdout.strip())
+    assert d["metric"] == "m" and "watchdog" in d["cfg5"]["error"] and d["cfg5"]["workload"] == "label"
+    other = subprocess.run([sys.executable, "-c", code, "1"], capture_output=True, text=True, timeout=25)
+    assert other.returncode == 0 and other.stdout.strip() == ""
+    t = bench.leg_watchdog(0.2, 0, {}, "x", "y")
+    t.cancel()
+    import time
+    time.sleep(0.4)  # still here: a cancelled timer does not fire
