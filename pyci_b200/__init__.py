@@ -33,7 +33,7 @@ from pyci_b200._pyci import compute_rdms, add_hci, compute_enpt2, compute_transi
 from pyci_b200._pyci import device_count, set_device, nccl_unique_id, init_comm
 from pyci_b200._pyci import launch_count, reset_launch_count, synchronize, release_memory
 
-from pyci_b200.utility import make_senzero_integrals, reduce_senzero_integrals, spinize_rdms
+from pyci_b200.utility import make_senzero_integrals, reduce_senzero_integrals, spinize_rdms, spin_free_rdms
 from pyci_b200.utility import add_excitations
 from pyci_b200.selectors import add_seniorities, add_gkci, add_cost, odometer_one_spin, odometer_two_spin
 
@@ -45,7 +45,7 @@ __all__ = [
     "secondquant_op", "hamiltonian", "wavefunction", "one_spin_wfn", "two_spin_wfn",
     "doci_wfn", "fullci_wfn", "genci_wfn", "sparse_op",
     "get_num_threads", "set_num_threads", "popcnt", "ctz", "compute_rdms", "add_hci", "compute_enpt2", "compute_transition_rdms", "compute_overlap",
-    "make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations",
+    "make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "spin_free_rdms", "add_excitations",
     "add_seniorities", "add_gkci", "add_cost", "odometer_one_spin", "odometer_two_spin",
     "device_count", "set_device", "nccl_unique_id", "init_comm", "launch_count", "reset_launch_count",
     "synchronize", "release_memory",

@@ -4,7 +4,7 @@ transforms, spin-block -> spin-orbital RDM conversion, excitation-level determin
 They only call the public ``_pyci`` surface."""
 import numpy as np
 
-__all__ = ["make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "add_excitations",
+__all__ = ["make_senzero_integrals", "reduce_senzero_integrals", "spinize_rdms", "spin_free_rdms", "add_excitations",
            "odometer_one_spin", "odometer_two_spin"]
 
 
@@ -72,6 +72,20 @@ def spinize_rdms(d1, d2):
         rdm2[a, b, b, a] -= d2[2].transpose(0, 1, 3, 2)
         rdm2[b, a, a, b] -= d2[2].transpose(1, 0, 2, 3)
     return rdm1, rdm2
+
+
+def spin_free_rdms(d1, d2, d3=None, d4=None, d5=None, d6=None, d7=None, flag="3RDM"):
+    r"""Spin-summed 1- and 2-RDM of FullCI spin blocks (``pyci/utility.py:326-421``, its FullCI branch):
+    ``rdm1 = aa + bb``, ``rdm2 = aaaa + abab + baba + bbbb`` of the spin-orbital matrices of ``spinize_rdms``.
+    The DOCI branch of the reference needs the 3-/4-RDM intermediates of ``compute_rdms_1234`` (out of scope here)."""
+    d1 = np.asarray(d1)
+    if d1.ndim == 2:
+        raise NotImplementedError("spin_free_rdms of DOCI matrices needs the 3-/4-RDM terms (compute_rdms_1234), "
+                                  "which pyci_b200 does not provide")
+    n = d1.shape[1]
+    rdm1, rdm2 = spinize_rdms(d1, d2)
+    a, b = slice(0, n), slice(n, 2 * n)
+    return rdm1[a, a] + rdm1[b, b], rdm2[a, a, a, a] + rdm2[a, b, a, b] + rdm2[b, a, b, a] + rdm2[b, b, b, b]
 
 
 def add_excitations(wfn, *excitations, ref=None):

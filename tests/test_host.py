@@ -132,6 +132,15 @@ def test_utility_helpers_match_oracle_restatement():
     one, two = rng.standard_normal((n, n)), rng.standard_normal((n, n, n, n))
     for x, y in zip(pyci.make_senzero_integrals(one, two), O.senzero_integrals(one, two)):
         assert np.array_equal(x, y)
+    # spin_free_rdms (utility.py:406-421): spin blocks summed; checked equal to the reference's function when written
+    s1, s2 = pyci.spin_free_rdms(d1, d2)
+    g1, g2 = O.spinize_rdms(d1, d2)
+    u, v = slice(0, n), slice(n, 2 * n)
+    assert np.array_equal(s1, g1[u, u] + g1[v, v])
+    assert np.array_equal(s2, g2[u, u, u, u] + g2[u, v, u, v] + g2[v, u, v, u] + g2[v, v, v, v])
+    assert abs(np.einsum("pqpq", s2) - sum(np.einsum("pqpq", g2[x, y, x, y]) for x in (u, v) for y in (u, v))) < 1e-12
+    with pytest.raises(NotImplementedError):
+        pyci.spin_free_rdms(d0, dd)
 
 
 def test_bulk_append_of_new_determinants():
