@@ -20,8 +20,9 @@ needs_suite = pytest.mark.skipif(not os.path.exists(os.path.join(SUITE, "test_ro
                                  reason="oracle/_ref/reftests not built (needs /root/reference at build time)")
 
 
-def run_suite(*args):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "reference_suite_runner.py"), SUITE, *args]
+def run_suite(*args, fanci=False):
+    where = ["--fanci", os.path.dirname(SUITE)] if fanci else [SUITE]
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "reference_suite_runner.py"), *where, *args]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
     assert r.returncode == 0, tail
@@ -46,3 +47,16 @@ def test_reference_routines_tests_pass_unchanged():
     absent = "he_ccpvqz or ((compute_rdms or transition_rdms) and (li2_ccpvdz or h2o_ccpvdz))"
     out = run_suite("test_routines.py", "test_odometer.py", "--durations=5", "-k", "not (%s)" % absent)
     assert " passed" in out and "failed" not in out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(SUITE), "fanci_test", "test_detratio.py")),
+                    reason="oracle/_ref/reftests/fanci_test not built (needs /root/reference at build time)")
+@pytest.mark.gpu
+def test_reference_fanci_detratio_tests_pass_unchanged():
+    """A caller of the path: the reference's FanCI base class and its DetRatio model, loaded from their
+    copies as `pyci.fanci`, build the rectangular operator `sparse_op(ham, wfn, nrow=nproj, ncol=len(wfn), symmetric=False)`
+    (fanci.py:203) and drive `op(x, out=...)` from scipy's least-squares solver (fanci.py:442,511).
+    pyci/fanci/test/test_detratio.py: objective and Jacobian against finite differences, and the DOCI ground-state energies
+    of Be/cc-pVDZ and LiH/6-31G reached through that operator.  The compiled reference passes the same 8 tests."""
+    out = run_suite("test_detratio.py", "--durations=3", fanci=True)
+    assert "8 passed" in out and "failed" not in out
