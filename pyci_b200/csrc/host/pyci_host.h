@@ -203,6 +203,10 @@ struct SparseOp {
     py::object dtype() const { return py::dtype::of<double>(); }
     long size() const { return handle ? pyci_op_size(handle) : 0; } // SparseOp::size, summed on the device at first use
     double get_element(long i, long j) const;
+    // SparseOp::perform_op / perform_op_symm (sparseop.cpp:96-112): y = A x on raw host pointers, the entry the reference's
+    // C++ callers use (FanCI objectives, fanci.cpp:144,196).  Full rows are stored, so both are the same product.
+    void perform_op(const double *x, double *y) const;
+    void perform_op_symm(const double *x, double *y) const { perform_op(x, y); }
     Array<double> py_matvec(const Array<double> x) const;
     Array<double> py_matvec_out(const Array<double> x, Array<double> y) const;
     py::tuple py_solve_ci(long n, py::object c0, long ncv, long maxiter, double tol);

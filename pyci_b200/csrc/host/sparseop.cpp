@@ -213,6 +213,8 @@ double SparseOp::get_element(long i, long j) const {
     return v;
 }
 
+void SparseOp::perform_op(const double *x, double *y) const { check(pyci_op_matvec(handle, x, y)); }
+
 Array<double> SparseOp::py_matvec(const Array<double> x) const {
     Array<double> y(nrow);
     return py_matvec_out(x, y);
