@@ -186,3 +186,38 @@ def test_selectors_against_the_reference_functions():
             sens = tuple(int(x) for x in rng.integers(0, nb + 2, int(rng.integers(1, 4))))
             both(lambda: m["seniority_ci"].add_seniorities(a, *sens), lambda: M.add_seniorities(b, *sens))
             assert same(a, b), ("seniority", args, sens)
+
+
+@needs_ref
+def test_hamiltonian_class_against_the_compiled_reference(tmp_path):
+    """secondquant_op from arrays (other dtypes, Fortran order, negative strides: pyci.h:161-165 forcecast), its derived
+    seniority-zero integrals, and FCIDUMP files written by either side: byte-identical files, identical objects read back by
+    the other side, same exception types.  (Arrays of the wrong shape are refused here with ValueError; the reference takes
+    them and reads past their end.)"""
+    rng = np.random.default_rng(3)
+    cmp = Pair()
+    for it in range(24):
+        n = int(rng.integers(1, 7))
+        one, two = rng.standard_normal((n, n)), rng.standard_normal((n, n, n, n))
+        if it % 4 == 1:
+            one = one.astype(np.float32)
+        elif it % 4 == 2:
+            two = np.asfortranarray(two)
+        elif it % 4 == 3:
+            one = one[:, ::-1]
+        ec = float(rng.standard_normal())
+        A, B = R.secondquant_op(ec, one, two), M.secondquant_op(ec, one, two)
+        for at in ("nbasis", "ecore", "one_mo", "two_mo", "h", "v", "w"):
+            cmp(at, lambda: getattr(A, at), lambda: getattr(B, at))
+        for k, kw in enumerate((dict(), dict(nelec=2, ms2=0), dict(nelec=3, ms2=1, tol=0.5), dict(tol=1e-3))):
+            fa, fb = str(tmp_path / ("a%d_%d.fcidump" % (it, k))), str(tmp_path / ("b%d_%d.fcidump" % (it, k)))
+            A.to_file(fa, **kw)
+            B.to_file(fb, **kw)
+            assert open(fa).read() == open(fb).read(), kw
+            CA, CB = R.secondquant_op(fb), M.secondquant_op(fa)
+            for at in ("nbasis", "ecore", "one_mo", "two_mo", "h", "v", "w"):
+                cmp("read back " + at, lambda: getattr(CA, at), lambda: getattr(CB, at))
+    cmp("missing file", lambda: R.secondquant_op("/nonexistent.fcidump"), lambda: M.secondquant_op("/nonexistent.fcidump"))
+    cmp("bad arguments", lambda: R.secondquant_op(1.0), lambda: M.secondquant_op(1.0))
+    with pytest.raises(ValueError):
+        M.secondquant_op(0.0, np.zeros((3, 4)), np.zeros((3, 3, 3, 3)))
