@@ -221,3 +221,31 @@ def test_hamiltonian_class_against_the_compiled_reference(tmp_path):
     cmp("bad arguments", lambda: R.secondquant_op(1.0), lambda: M.secondquant_op(1.0))
     with pytest.raises(ValueError):
         M.secondquant_op(0.0, np.zeros((3, 4)), np.zeros((3, 3, 3, 3)))
+
+
+@needs_ref
+def test_wavefunction_files_are_interchangeable_with_the_compiled_reference(tmp_path):
+    """to_file / file constructors (onespinwfn.cpp:60-104, twospinwfn.cpp:60-107): byte-identical files, each side reads
+    the other's, reading a file with another class behaves alike, a missing file raises the same error."""
+    for k, (kind, args) in enumerate((("doci", (10, 3, 3)), ("doci", (70, 2, 2)), ("fullci", (8, 3, 2)), ("fullci", (130, 2, 1)),
+                                      ("genci", (12, 4, 0)), ("genci", (65, 3, 0)), ("fullci", (6, 2, 0)))):
+        a, b = getattr(R, kind + "_wfn")(*args), getattr(M, kind + "_wfn")(*args)
+        for w in (a, b):
+            w.add_hartreefock_det()
+            w.add_excited_dets(1)
+            w.add_excited_dets(2)
+        fa, fb = str(tmp_path / ("a%d.bin" % k)), str(tmp_path / ("b%d.bin" % k))
+        a.to_file(fa)
+        b.to_file(fb)
+        assert open(fa, "rb").read() == open(fb, "rb").read()
+        ca, cb = getattr(R, kind + "_wfn")(fb), getattr(M, kind + "_wfn")(fa)
+        assert len(ca) == len(cb) == len(a) and np.array_equal(ca.to_det_array(), cb.to_det_array())
+        cmp = Pair()
+        for other in ("doci", "fullci", "genci"):
+            def load(P, other=other):
+                x = getattr(P, other + "_wfn")(fa)
+                return (len(x), x.nbasis, x.nocc_up, x.nocc_dn)
+            cmp("%s file as %s" % (kind, other), lambda: load(R), lambda: load(M))
+    for P in (R, M):
+        with pytest.raises(RuntimeError, match="iostream error"):
+            P.doci_wfn("/nonexistent")
