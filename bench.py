@@ -498,8 +498,10 @@ def reduce_parity(B, g):
 
 
 def golden_e0(spec):
-    """E0 of the oracle-built operator by ARPACK (tests/golden/e0_syn.json, made by tests/golden/make_golden_e0.py),
-    or the energies the reference's own tests pin (pyci/test/test_routines.py:44-45)."""
+    """E0 of the oracle-built operator by ARPACK (tests/golden/e0_syn.json, made by tests/golden/make_golden_e0.py; for
+    config 4, whose matrix does not fit a CPU box, by the string-driven direct-CI product of make_golden_e0_direct.py,
+    which reproduces the matrix-based goldens of the smaller sizes), or the energies the reference's own tests pin
+    (pyci/test/test_routines.py:44-45)."""
     if spec.get("key") == "cfg1":
         return -14.617409507, 1e-9, "pyci/test/test_routines.py:44 (atol 1e-9)"
     if spec.get("key") == "cfg2":
@@ -509,7 +511,8 @@ def golden_e0(spec):
             with open(os.path.join(ROOT, "tests", "golden", "e0_syn.json")) as f:
                 g = json.load(f).get("syn%d" % spec["n"])
             if g and tuple(g["occ"]) == tuple(spec["occ"]):
-                return g["E0"], 1e-10, "tests/golden/e0_syn.json (oracle-built operator + ARPACK, %d matvecs)" % g["arpack_matvecs"]
+                how = "string-driven direct CI" if g.get("operator", "").startswith("string-driven") else "oracle-built operator"
+                return g["E0"], 1e-10, "tests/golden/e0_syn.json (%s + ARPACK, %d matvecs)" % (how, g["arpack_matvecs"])
         except (OSError, ValueError):
             pass
     return None, None, None

@@ -75,8 +75,12 @@ def test_golden_e0_lookup():
     spec = bench.workload_spec("cfg1")
     spec["key"] = "cfg1"
     assert bench.golden_e0(spec)[0] == -14.617409507  # pyci/test/test_routines.py:44
-    spec = bench.workload_spec("cfg4")
+    spec = bench.workload_spec("cfg4")   # the matrix does not fit a CPU box: string-driven direct CI (make_golden_e0_direct.py)
     spec["key"] = "cfg4"
+    e0, tol, src = bench.golden_e0(spec)
+    assert abs(e0 - (-34.525629697)) < 1e-8 and tol == 1e-10 and "direct CI" in src
+    spec = bench.workload_spec("cfg5")
+    spec["key"] = "cfg5"
     assert bench.golden_e0(spec) == (None, None, None)
 
 
