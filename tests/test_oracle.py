@@ -286,3 +286,22 @@ def test_oracle_update_equals_reference(update_golden, tag, fn, kind, occ, mode,
         fresh = O.sparse_op(okind, one.shape[0], occ[0], occ[1], dets, ints, symmetric=False)
         assert len(fresh[1]) > len(ix)
 
+
+
+def test_direct_ci_generator_of_the_cfg4_energy():
+    """tests/golden/make_golden_e0_direct.py (the string-driven product behind the cfg4 entry of e0_syn.json): its product
+    equals the oracle's FullCI matrix on a random vector, and its E0 of syn8 equals the matrix-based golden."""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden_e0_direct", os.path.join(GOLDEN, "make_golden_e0_direct.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert m.self_test(6) < 1e-13
+    with open(os.path.join(GOLDEN, "e0_syn.json")) as f:
+        gold = json.load(f)
+    r = m.lowest(8)
+    assert abs(r["E0"] - gold["syn8"]["E0"]) < 1e-11 and r["ndet"] == gold["syn8"]["ndet"]
+    assert abs(gold["syn14"]["direct_ci_E0"] - gold["syn14"]["E0"]) < 1e-11  # recorded when the cfg4 entry was made
+    assert gold["syn16"]["operator"].startswith("string-driven") and gold["syn16"]["ndet"] == 3312400
