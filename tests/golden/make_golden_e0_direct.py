@@ -16,6 +16,10 @@ goldens already in e0_syn.json (syn8/10/12/14) -- that is its own check -- and t
 
     python tests/golden/make_golden_e0_direct.py --check 8 10 12      # |E0 - golden| of the sizes that have one
     python tests/golden/make_golden_e0_direct.py 16                   # ~14 GB of RAM, about half an hour on 8 cores
+    python tests/golden/make_golden_e0_direct.py --spmv 14 16         # -> tests/golden/spmv_direct.npz
+
+--spmv: y = H x of a seeded x (conftest.seeded_vec(ndet, 8)) by the same product, kept as 4096 sampled entries plus
+|y| and x.y -- the fixture the full-size SpMV of the device is compared with (tests/test_zz_independent_product.py).
 """
 import json
 import os
@@ -119,7 +123,28 @@ def self_test(n=6):
     return err
 
 
+def spmv_fixture(sizes):
+    out = {}
+    for n in sizes:
+        H = DirectCI(n)
+        nd = H.ns * H.ns
+        x = np.random.default_rng(8).standard_normal(nd)  # = tests/conftest.py seeded_vec(nd, 8)
+        t0 = time.perf_counter()
+        y = H.matvec(x)
+        idx = np.sort(np.random.default_rng(n).choice(nd, 4096, replace=False))
+        idx[0], idx[-1] = 0, nd - 1
+        key = "syn%d" % n
+        out[key + ".idx"], out[key + ".y"] = idx.astype(np.int64), y[idx]
+        out[key + ".norm"], out[key + ".xdoty"], out[key + ".xnorm"] = np.linalg.norm(y), float(x @ y), np.linalg.norm(x)
+        print("%s: %d determinants, |y| %.15e, x.y %.15e, %.1f s" % (key, nd, out[key + ".norm"], out[key + ".xdoty"],
+                                                                     time.perf_counter() - t0), flush=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "spmv_direct.npz"), **out)
+
+
 def main(argv):
+    if "--spmv" in argv:
+        print("self test (n = 6): rel err %.1e" % self_test(), flush=True)
+        return spmv_fixture([int(a) for a in argv if a.isdigit()])
     check = "--check" in argv
     sizes = [int(a) for a in argv if a.isdigit()]
     print("self test (n = 6, product against the oracle's matrix): rel err %.1e" % self_test(), flush=True)
