@@ -305,3 +305,29 @@ def test_direct_ci_generator_of_the_cfg4_energy():
     assert abs(r["E0"] - gold["syn8"]["E0"]) < 1e-11 and r["ndet"] == gold["syn8"]["ndet"]
     assert abs(gold["syn14"]["direct_ci_E0"] - gold["syn14"]["E0"]) < 1e-11  # recorded when the cfg4 entry was made
     assert gold["syn16"]["operator"].startswith("string-driven") and gold["syn16"]["ndet"] == 3312400
+
+
+@pytest.mark.parametrize("K,P,nd", [(8, 3, 56), (10, 3, 100), (16, 5, 3000)])
+def test_config5_style_genci_operator_equals_the_reference_doci_operator(K, P, nd):
+    """Config 5's spaces are seniority-zero selections inside a GenCI spin-orbital space.  The reference's GenCI kernels
+    are defective, its DOCI kernels are not: between closed-shell determinants only pair
+    excitations survive, with element <kk|ll> = v[k,l], and the diagonal is the DOCI diagonal.  So the oracle's GenCI
+    operator over spin-orbital integrals must equal the COMPILED REFERENCE's DOCI operator over the pair strings: same
+    structure bit for bit, data to rounding (the sums run in a different order) -- a pin of the config-5 parity chain
+    (device == oracle bit for bit) on the reference's own code."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref"))
+    R = pytest.importorskip("pyci_ref")
+    from pyci_b200.synthetic import seniority_zero_genci_dets
+    ecore, one, two = O.synthetic_integrals(K, 77)
+    hs, gs = O.spin_orbital_integrals(one, two)
+    dets = seniority_zero_genci_dets(K, P, nd)
+    pair = (dets[:, 0] & np.uint64((1 << K) - 1)).reshape(-1, 1).copy()
+    assert np.array_equal(dets[:, 0], pair[:, 0] | (pair[:, 0] << np.uint64(K)))
+    for sym in (True, False):
+        ip, ix, dv = O.sparse_op(O.GENCI, 2 * K, 2 * P, 0, dets, (hs, gs), symmetric=sym)
+        op = R.sparse_op(R.secondquant_op(ecore, one, two), R.doci_wfn(K, P, P, pair), symmetric=sym)
+        assert np.array_equal(ip, op.indptr()) and np.array_equal(ix, op.indices())
+        ref = op.data()
+        assert np.max(np.abs(dv - ref)) <= 1e-13 * np.max(np.abs(ref))
